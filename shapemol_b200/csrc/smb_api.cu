@@ -1,0 +1,262 @@
+// extern "C" entry points that enqueue work: kNN graph, one network evaluation, one reverse step.
+#include "smb_common.cuh"
+#include "smb_kernels.h"
+
+namespace smb {
+
+static int check_batch(const smb_batch* b) {
+  if (!b) { set_error_msg("null batch"); return SMB_E_BADARG; }
+  if (b->n_atoms < 0 || b->n_mols < 0) { set_error_msg("negative batch size"); return SMB_E_BADARG; }
+  if (b->n_atoms > 0 && (!b->mol_ptr || !b->atom_mol)) { set_error_msg("null mol_ptr / atom_mol"); return SMB_E_BADARG; }
+  if (b->max_atoms_per_mol > SMB_MAX_ATOMS_PER_MOL) { set_error_msg("molecule larger than SMB_MAX_ATOMS_PER_MOL"); return SMB_E_TOOBIG; }
+  return 0;
+}
+
+static inline const float* fptr(const void* base, size_t off) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(base) + off);
+}
+static inline const void* vptr(const void* base, size_t off) {
+  return reinterpret_cast<const unsigned char*>(base) + off;
+}
+template <class T>
+static inline T* wptr(void* base, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(base) + off); }
+
+static void fill_edge_weights(EdgeArgs& e, const void* blob, const EdgeMlpOff& o) {
+  e.w1r = vptr(blob, o.w1r); e.b1 = fptr(blob, o.b1); e.ln_g = fptr(blob, o.ln_g); e.ln_b = fptr(blob, o.ln_b);
+  e.w2 = vptr(blob, o.w2); e.b2 = fptr(blob, o.b2);
+}
+static void fill_node_weights(NodeArgs& n, const void* blob, const NodeMlpOff& o) {
+  n.w1 = vptr(blob, o.w1); n.b1 = fptr(blob, o.b1); n.ln_g = fptr(blob, o.ln_g); n.ln_b = fptr(blob, o.ln_b);
+  n.w2 = vptr(blob, o.w2); n.b2 = fptr(blob, o.b2);
+}
+
+#define SMB_LAUNCH(expr)                                                                     \
+  do {                                                                                       \
+    int _rc = (expr);                                                                        \
+    if (_rc != 0) { if (_rc > 0) set_error(#expr, (cudaError_t)_rc); return _rc; }           \
+  } while (0)
+
+static int forward_impl(const smb_model_dims& d, const void* blob, const smb_batch& b, const smb_forward_io& io, void* ws_base,
+                        size_t ws_bytes, cudaStream_t st) {
+  const int N = b.n_atoms, B = b.n_mols, H = d.hidden;
+  const Workspace W = build_workspace(d, N, B);
+  if (ws_bytes < W.total || !ws_base) { set_error_msg("smb_forward: workspace too small"); return SMB_E_BADARG; }
+  if (!io.pos || !io.v || !io.shape || !io.t || !io.pred_pos || !io.pred_h || !io.pred_v) {
+    set_error_msg("smb_forward: null io pointer");
+    return SMB_E_BADARG;
+  }
+  for (int l = 0; l < d.layers; ++l)
+    if (!io.bn_weight[l] || !io.bn_bias[l] || !io.bn_running_mean[l] || !io.bn_running_var[l]) {
+      set_error_msg("smb_forward: null BatchNorm pointer");
+      return SMB_E_BADARG;
+    }
+  if (N == 0) return 0;
+  const ModelLayout L = build_layout(d);
+  const int n_max = b.max_atoms_per_mol > 0 ? b.max_atoms_per_mol : SMB_MAX_ATOMS_PER_MOL;
+
+  float* x = wptr<float>(ws_base, W.x);
+  float* tau = wptr<float>(ws_base, W.tau);
+  float* inv = wptr<float>(ws_base, W.inv);
+  int* nbr = wptr<int>(ws_base, W.nbr);
+  int* deg = wptr<int>(ws_base, W.deg);
+  float* ew = wptr<float>(ws_base, W.ew);
+  float* alpha = wptr<float>(ws_base, W.alpha);
+  float* hbuf[2] = {wptr<float>(ws_base, W.h_a), wptr<float>(ws_base, W.h_b)};
+  float* ab = wptr<float>(ws_base, W.ab);
+  float* q = wptr<float>(ws_base, W.q);
+  float* agg = wptr<float>(ws_base, W.agg);
+  float* vn = wptr<float>(ws_base, W.vn);
+  float* bn_part = wptr<float>(ws_base, W.bn_part);
+  float* bn_param = wptr<float>(ws_base, W.bn_param);
+
+  SMB_CUDA_OK(cudaMemcpyAsync(x, io.pos, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  PrepArgs pa;
+  pa.n_mols = B; pa.t = io.t; pa.shape = io.shape;
+  pa.time_freq = fptr(blob, L.time_freq); pa.time_w1 = fptr(blob, L.time_w1); pa.time_b1 = fptr(blob, L.time_b1);
+  pa.time_w2 = fptr(blob, L.time_w2); pa.time_b2 = fptr(blob, L.time_b2);
+  pa.inv_w1 = fptr(blob, L.inv_w1); pa.inv_b1 = fptr(blob, L.inv_b1); pa.inv_g = fptr(blob, L.inv_g);
+  pa.inv_bb = fptr(blob, L.inv_bb); pa.inv_w2 = fptr(blob, L.inv_w2); pa.inv_b2 = fptr(blob, L.inv_b2);
+  pa.tau = tau; pa.inv = inv;
+  SMB_LAUNCH(launch_prep(pa, st));
+
+  EmbedArgs ea;
+  ea.n_atoms = N; ea.H = H; ea.classes = d.classes; ea.v = io.v; ea.atom_mol = b.atom_mol; ea.tau = tau;
+  ea.emb_wT = fptr(blob, L.emb_wT); ea.emb_b = fptr(blob, L.emb_b); ea.h = hbuf[0]; ea.h0 = io.h0;
+  SMB_LAUNCH(launch_embed(ea, st));
+
+  SMB_LAUNCH(launch_knn(x, b.mol_ptr, B, d.k, nbr, deg, st));
+  if (io.nbr) SMB_CUDA_OK(cudaMemcpyAsync(io.nbr, nbr, (size_t)N * (d.k + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+
+  EdgeArgs eb;
+  memset(&eb, 0, sizeof(eb));
+  eb.n_mols = B; eb.n_max = n_max; eb.k = d.k; eb.mol_ptr = b.mol_ptr; eb.x = x; eb.nbr = nbr; eb.deg = deg;
+  eb.ab = ab; eb.q = q; eb.ew_in = ew; eb.ew_out = ew; eb.alpha = alpha; eb.agg = agg; eb.shape = io.shape; eb.vn = vn;
+  eb.bn_partial = bn_part;
+
+  {  // global edge gate, computed once from the input coordinates (uni_transformer.py:507)
+    EdgeArgs e = eb;
+    fill_edge_weights(e, blob, L.gate);
+    SMB_LAUNCH(launch_edge(d, ROLE_GATE, e, nullptr, st));
+  }
+
+  int cur = 0;
+  for (int l = 0; l < d.layers; ++l) {
+    const LayerOff& y = L.layer[l];
+    const bool last = l == d.layers - 1;
+    float* h_in = hbuf[cur];
+    float* h_out = last ? io.pred_h : hbuf[cur ^ 1];
+    NodeArgs na;
+    memset(&na, 0, sizeof(na));
+    na.n_atoms = N; na.atom_mol = b.atom_mol;
+    // ---- X2H ----
+    {
+      NodeArgs n = na;
+      n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
+      n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
+      fill_node_weights(n, blob, y.x2h_pre);
+      SMB_LAUNCH(launch_node_mlp(d, n, st));
+    }
+    {
+      EdgeArgs e = eb;
+      e.col_a = 0; e.col_b = H;
+      fill_edge_weights(e, blob, y.hk);
+      SMB_LAUNCH(launch_edge(d, ROLE_K, e, nullptr, st));
+    }
+    {
+      EdgeArgs e = eb;
+      e.col_a = 2 * H; e.col_b = 3 * H;
+      fill_edge_weights(e, blob, y.hv);
+      SMB_LAUNCH(launch_edge(d, ROLE_V, e, nullptr, st));
+    }
+    {
+      NodeArgs n = na;
+      n.x_mode = XMODE_AGG_H; n.act = ACT_LN_RELU; n.n_pass = 0; n.n2 = H; n.n2_valid = H;
+      n.xa = agg; n.xb = h_in; n.residual = h_in; n.out2 = h_out;
+      fill_node_weights(n, blob, y.node_out);
+      SMB_LAUNCH(launch_node_mlp(d, n, st));
+    }
+    // ---- H2X (uses the updated h) ----
+    {
+      NodeArgs n = na;
+      n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
+      n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
+      fill_node_weights(n, blob, y.h2x_pre);
+      SMB_LAUNCH(launch_node_mlp(d, n, st));
+    }
+    {
+      EdgeArgs e = eb;
+      e.col_a = 0; e.col_b = H;
+      fill_edge_weights(e, blob, y.xk);
+      SMB_LAUNCH(launch_edge(d, ROLE_K, e, nullptr, st));
+    }
+    int grid = 0;
+    {
+      EdgeArgs e = eb;
+      e.col_a = 2 * H; e.col_b = 3 * H;
+      e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
+      fill_edge_weights(e, blob, y.xv);
+      SMB_LAUNCH(launch_edge(d, ROLE_XV, e, &grid, st));
+    }
+    {
+      BnArgs bn;
+      bn.training = io.training; bn.n_atoms = N; bn.rows = grid * kEdgeWarps; bn.partial = bn_part;
+      bn.weight = io.bn_weight[l]; bn.bias = io.bn_bias[l];
+      bn.running_mean = io.bn_running_mean[l]; bn.running_var = io.bn_running_var[l];
+      bn.num_batches_tracked = io.bn_num_batches_tracked[l];
+      bn.param = bn_param;
+      SMB_LAUNCH(launch_bn_final(bn, st));
+    }
+    SMB_LAUNCH(launch_vn_apply(vn, bn_param, x, last ? io.pred_pos : nullptr, N, st));
+    cur ^= 1;
+  }
+  {  // type head (molopt_score_model.py:305)
+    NodeArgs n;
+    memset(&n, 0, sizeof(n));
+    n.n_atoms = N; n.atom_mol = b.atom_mol;
+    n.x_mode = XMODE_H; n.act = ACT_SSP; n.n_pass = 0; n.n2 = 16; n.n2_valid = d.classes;
+    n.xa = io.pred_h; n.out2 = io.pred_v;
+    fill_node_weights(n, blob, L.head);
+    SMB_LAUNCH(launch_node_mlp(d, n, st));
+  }
+  return 0;
+}
+
+}  // namespace smb
+
+extern "C" {
+
+int smb_knn_graph(const float* x, const smb_batch* batch, int32_t k, int32_t* nbr, int32_t* deg, void* stream) {
+  int rc = smb::check_batch(batch);
+  if (rc) return rc;
+  if (k < 1 || k > SMB_MAX_K) { smb::set_error_msg("smb_knn_graph: k out of range"); return SMB_E_TOOBIG; }
+  if (batch->n_atoms == 0) return 0;
+  if (!x || !nbr || !deg) { smb::set_error_msg("smb_knn_graph: null pointer"); return SMB_E_BADARG; }
+  rc = smb::launch_knn(x, batch->mol_ptr, batch->n_mols, k, nbr, deg, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("knn_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
+int smb_forward(const smb_model_dims* dims, const void* packed_weights_dev, const smb_batch* batch, const smb_forward_io* io,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dims || !packed_weights_dev || !io) { smb::set_error_msg("smb_forward: null argument"); return SMB_E_BADARG; }
+  int rc = smb::check_dims(*dims);
+  if (rc) return rc;
+  rc = smb::check_batch(batch);
+  if (rc) return rc;
+  return smb::forward_impl(*dims, packed_weights_dev, *batch, *io, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int smb_type_head(const smb_model_dims* dims, const void* packed_weights_dev, const smb_batch* batch, const float* h,
+                  float* logits, void* stream) {
+  if (!dims || !packed_weights_dev || !h || !logits) { smb::set_error_msg("smb_type_head: null argument"); return SMB_E_BADARG; }
+  int rc = smb::check_dims(*dims);
+  if (rc) return rc;
+  rc = smb::check_batch(batch);
+  if (rc) return rc;
+  const smb::ModelLayout L = smb::build_layout(*dims);
+  smb::NodeArgs n;
+  memset(&n, 0, sizeof(n));
+  n.n_atoms = batch->n_atoms; n.atom_mol = batch->atom_mol;
+  n.x_mode = smb::XMODE_H; n.act = smb::ACT_SSP; n.n_pass = 0; n.n2 = 16; n.n2_valid = dims->classes;
+  n.xa = h; n.out2 = logits;
+  smb::fill_node_weights(n, packed_weights_dev, L.head);
+  rc = smb::launch_node_mlp(*dims, n, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("node_mlp_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
+int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batch, const smb_posterior_io* io, void* stream) {
+  if (!dims || !io) { smb::set_error_msg("smb_posterior_step: null argument"); return SMB_E_BADARG; }
+  int rc = smb::check_dims(*dims);
+  if (rc) return rc;
+  rc = smb::check_batch(batch);
+  if (rc) return rc;
+  if (batch->n_atoms == 0) return 0;
+  if (!io->pred_pos || !io->pred_v || !io->t || !io->pos || !io->v || !io->posterior_mean_c0_coef || !io->posterior_mean_ct_coef ||
+      !io->posterior_logvar || !io->log_alphas_v || !io->log_one_minus_alphas_v || !io->log_alphas_cumprod_v ||
+      !io->log_one_minus_alphas_cumprod_v || ((io->noise_pos == nullptr) != (io->noise_u == nullptr))) {
+    smb::set_error_msg("smb_posterior_step: null io pointer (noise_pos and noise_u must both be given or both be NULL)");
+    return SMB_E_BADARG;
+  }
+  smb::PosteriorArgs a;
+  a.n_atoms = batch->n_atoms; a.classes = dims->classes; a.atom_mol = batch->atom_mol; a.t = io->t;
+  a.pred_pos = io->pred_pos; a.pred_v = io->pred_v; a.pos = io->pos; a.v = io->v;
+  a.noise_pos = io->noise_pos; a.noise_u = io->noise_u; a.log_v0 = io->log_v0; a.log_post = io->log_post;
+  a.seed = io->seed; a.atom_offset = io->atom_offset;
+  a.c0 = io->posterior_mean_c0_coef; a.ct = io->posterior_mean_ct_coef; a.logvar = io->posterior_logvar;
+  a.log_a = io->log_alphas_v; a.log_1m_a = io->log_one_minus_alphas_v;
+  a.log_ac = io->log_alphas_cumprod_v; a.log_1m_ac = io->log_one_minus_alphas_cumprod_v;
+  rc = smb::launch_posterior(a, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("posterior_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
+int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream) {
+  if (n_mols > 0 && !t) { smb::set_error_msg("smb_decrement_t: null pointer"); return SMB_E_BADARG; }
+  int rc = smb::launch_decrement_t(t, n_mols, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("decrement_t launch", (cudaError_t)rc);
+  return rc;
+}
+
+}  // extern "C"

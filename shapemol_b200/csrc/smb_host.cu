@@ -1,0 +1,335 @@
+// Host side of the C ABI: error reporting, parameter enumeration, weight packing, workspace layout.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+
+#include "smb_common.cuh"
+#include "smb_layout.h"
+
+namespace smb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s failed: %s (%d)", what, cudaGetErrorString(e), (int)e);
+}
+void set_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
+int check_dims(const smb_model_dims& d) {
+  if (d.hidden != 128) { set_error_msg("hidden_dim must be 128 (256 is not built yet)"); return SMB_E_UNSUPPORTED; }
+  if (d.heads != kHeads) { set_error_msg("n_heads must be 16"); return SMB_E_UNSUPPORTED; }
+  if (d.layers < 1 || d.layers > kMaxLayers) { set_error_msg("num_layers out of range"); return SMB_E_UNSUPPORTED; }
+  if (d.k < 1 || d.k > SMB_MAX_K) { set_error_msg("knn out of range (1..63)"); return SMB_E_TOOBIG; }
+  if (d.classes < 2 || d.classes > 16) { set_error_msg("num classes must be <= 16"); return SMB_E_UNSUPPORTED; }
+  if (d.time_dim != 8) { set_error_msg("time_emb_dim must be 8"); return SMB_E_UNSUPPORTED; }
+  if (d.precision != SMB_PREC_BF16X3 && d.precision != SMB_PREC_BF16) { set_error_msg("bad precision"); return SMB_E_BADARG; }
+  if (d.timesteps < 1) { set_error_msg("bad timesteps"); return SMB_E_BADARG; }
+  return 0;
+}
+
+// ---- layout ---------------------------------------------------------------------------------
+namespace {
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; }
+};
+
+EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
+  const int H = d.hidden;
+  const size_t fb = frag_bytes(d);
+  EdgeMlpOff e;
+  e.w1r = c.take((size_t)(H / 8) * 2 * 32 * fb);
+  e.b1 = c.take(H * 4);
+  e.ln_g = c.take(H * 4);
+  e.ln_b = c.take(H * 4);
+  e.w2 = gate ? c.take(H * 4) : c.take((size_t)(n2 / 8) * (H / 16) * 32 * fb);
+  e.b2 = c.take((gate ? 4 : n2) * 4);
+  return e;
+}
+NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2) {
+  const int H = d.hidden;
+  const size_t fb = frag_bytes(d);
+  NodeMlpOff n;
+  n.w1 = c.take((size_t)(n1 / 8) * (k1 / 16) * 32 * fb);
+  n.b1 = c.take(n1 * 4);
+  n.ln_g = c.take(H * 4);
+  n.ln_b = c.take(H * 4);
+  n.w2 = c.take((size_t)(n2 / 8) * (H / 16) * 32 * fb);
+  n.b2 = c.take(n2 * 4);
+  return n;
+}
+}  // namespace
+
+ModelLayout build_layout(const smb_model_dims& d) {
+  const int H = d.hidden;
+  Carver c;
+  ModelLayout L;
+  memset(&L, 0, sizeof(L));
+  L.time_freq = c.take(d.time_dim / 2 * 4);
+  L.time_w1 = c.take(d.time_dim * 2 * d.time_dim * 4);
+  L.time_b1 = c.take(d.time_dim * 2 * 4);
+  L.time_w2 = c.take(d.time_dim * d.time_dim * 2 * 4);
+  L.time_b2 = c.take(d.time_dim * 4);
+  L.emb_wT = c.take((size_t)(d.classes + d.time_dim) * H * 4);
+  L.emb_b = c.take(H * 4);
+  L.inv_w1 = c.take(kShape * kShape * 4);
+  L.inv_b1 = c.take(kShape * 4);
+  L.inv_g = c.take(kShape * 4);
+  L.inv_bb = c.take(kShape * 4);
+  L.inv_w2 = c.take(kShape * kShape * 4);
+  L.inv_b2 = c.take(kShape * 4);
+  L.gate = carve_edge(c, d, 0, true);
+  L.head = carve_node(c, d, H, H, 16);
+  for (int l = 0; l < d.layers; ++l) {
+    LayerOff& y = L.layer[l];
+    y.hk = carve_edge(c, d, H, false);
+    y.hv = carve_edge(c, d, H, false);
+    y.xk = carve_edge(c, d, H, false);
+    y.xv = carve_edge(c, d, kHeads, false);
+    y.x2h_pre = carve_node(c, d, 5 * H, H + kShape, H);
+    y.node_out = carve_node(c, d, H, 2 * H, H);
+    y.h2x_pre = carve_node(c, d, 5 * H, H + kShape, H);
+    y.vn_feat = c.take(kHeads * kVnStride * 4);
+    y.vn_dir = c.take(kHeads * kVnStride * 4);
+  }
+  L.total = c.off;
+  return L;
+}
+
+Workspace build_workspace(const smb_model_dims& d, int N, int B) {
+  const int H = d.hidden, KS = d.k + 1;
+  Carver c;
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  const size_t n = (size_t)(N > 0 ? N : 1), b = (size_t)(B > 0 ? B : 1);
+  w.tau = c.take(b * 8 * 4);
+  w.inv = c.take(b * kShape * 4);
+  w.nbr = c.take(n * KS * 4);
+  w.deg = c.take(n * 4);
+  w.ew = c.take(n * KS * 4);
+  w.alpha = c.take(n * KS * kHeads * 4);
+  w.x = c.take(n * 3 * 4);
+  w.h_a = c.take(n * H * 4);
+  w.h_b = c.take(n * H * 4);
+  w.ab = c.take(n * 4 * H * 4);
+  w.q = c.take(n * H * 4);
+  w.agg = c.take(n * H * 4);
+  w.vn = c.take(n * kVnRow * 4);
+  w.bn_part_rows = kEdgeMaxCtas * kEdgeWarps;
+  w.bn_part = c.take((size_t)w.bn_part_rows * 32 * 4);
+  w.bn_param = c.take(32 * 4);
+  w.total = c.off;
+  return w;
+}
+
+// ---- parameter enumeration --------------------------------------------------------------------
+const std::vector<std::string>& param_names(const smb_model_dims& d) {
+  static std::mutex mu;
+  static std::map<int, std::vector<std::string>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(d.layers);
+  if (it != cache.end()) return it->second;
+  std::vector<std::string> v;
+  const char* six[6] = {"0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias"};
+  auto add_mlp = [&](const std::string& p) { for (auto s : six) v.push_back(p + ".net." + s); };
+  v.push_back("time_emb.1.weight"); v.push_back("time_emb.1.bias");
+  v.push_back("time_emb.3.weight"); v.push_back("time_emb.3.bias");
+  v.push_back("ligand_atom_emb.weight"); v.push_back("ligand_atom_emb.bias");
+  add_mlp("refine_net.edge_pred_layer");
+  add_mlp("refine_net.invariant_shape_layer.hidden_layer");
+  v.push_back("v_inference.0.weight"); v.push_back("v_inference.0.bias");
+  v.push_back("v_inference.2.weight"); v.push_back("v_inference.2.bias");
+  for (int l = 0; l < d.layers; ++l) {
+    std::string b = "refine_net.base_block." + std::to_string(l);
+    for (auto m : {"hk_func", "hv_func", "hq_func", "node_output"}) add_mlp(b + ".x2h_layers.0." + m);
+    for (auto m : {"xk_func", "xv_func", "xq_func"}) add_mlp(b + ".h2x_layers.0." + m);
+    v.push_back(b + ".h2x_layers.0.shape_linear.map_to_feat.weight");
+    v.push_back(b + ".h2x_layers.0.shape_linear.map_to_dir.weight");
+  }
+  return cache.emplace(d.layers, std::move(v)).first->second;
+}
+
+// ---- packing ----------------------------------------------------------------------------------
+namespace {
+inline uint16_t f2bf(float f) {   // round-to-nearest-even
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+// B fragments of mma.m16n8k16 for B[k][n] = W(n,k): per (n-tile, k-step, lane) the four values
+// (k=2t,2t+1 | k=2t+8,2t+9) at n = 8*nt+g, as bf16 hi (and lo) pairs.
+template <class F>
+void pack_frags(uint8_t* dst, int NT, int KS, int prec, F W) {
+  const size_t fb = prec == SMB_PREC_BF16X3 ? 16 : 8;
+  for (int nt = 0; nt < NT; ++nt)
+    for (int ks = 0; ks < KS; ++ks)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, k0 = ks * 16 + 2 * t;
+        const float v[4] = {W(n, k0), W(n, k0 + 1), W(n, k0 + 8), W(n, k0 + 9)};
+        uint16_t hi[4], lo[4];
+        for (int i = 0; i < 4; ++i) { hi[i] = f2bf(v[i]); lo[i] = f2bf(v[i] - bf2f(hi[i])); }
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst + ((size_t)(nt * KS + ks) * 32 + lane) * fb);
+        o[0] = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16);
+        o[1] = (uint32_t)hi[2] | ((uint32_t)hi[3] << 16);
+        if (prec == SMB_PREC_BF16X3) {
+          o[2] = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16);
+          o[3] = (uint32_t)lo[2] | ((uint32_t)lo[3] << 16);
+        }
+      }
+}
+inline void put(uint8_t* blob, size_t off, const float* src, size_t n) { memcpy(blob + off, src, n * 4); }
+}  // namespace
+
+static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* blob) {
+  const int H = d.hidden, C = d.classes, TD = d.time_dim, prec = d.precision;
+  const int KV = 2 * H + kRbf + kShape;   // 308: [r | h_dst | h_src | inv]
+  const ModelLayout L = build_layout(d);
+  memset(blob, 0, L.total);
+  const std::vector<std::string>& names = param_names(d);
+  std::map<std::string, const float*> P;
+  for (size_t i = 0; i < names.size(); ++i) P[names[i]] = hp[i];
+  auto get = [&](const std::string& k) -> const float* { return P.at(k); };
+
+  // time embedding: frequencies exp(-j ln(1e4)/(half-1))  (models/molopt_score_model.py:159-166)
+  {
+    float* f = reinterpret_cast<float*>(blob + L.time_freq);
+    const int half = TD / 2;
+    const float e = (float)(log(10000.0) / (half - 1));
+    for (int j = 0; j < half; ++j) f[j] = expf((float)j * -e);
+    put(blob, L.time_w1, get("time_emb.1.weight"), 2 * TD * TD);
+    put(blob, L.time_b1, get("time_emb.1.bias"), 2 * TD);
+    put(blob, L.time_w2, get("time_emb.3.weight"), TD * 2 * TD);
+    put(blob, L.time_b2, get("time_emb.3.bias"), TD);
+  }
+  {  // atom embedding, transposed to [in][H]
+    const float* w = get("ligand_atom_emb.weight");
+    float* o = reinterpret_cast<float*>(blob + L.emb_wT);
+    const int in = C + TD;
+    for (int c = 0; c < H; ++c) for (int k = 0; k < in; ++k) o[(size_t)k * H + c] = w[(size_t)c * in + k];
+    put(blob, L.emb_b, get("ligand_atom_emb.bias"), H);
+  }
+  {
+    const std::string p = "refine_net.invariant_shape_layer.hidden_layer.net.";
+    put(blob, L.inv_w1, get(p + "0.weight"), kShape * kShape); put(blob, L.inv_b1, get(p + "0.bias"), kShape);
+    put(blob, L.inv_g, get(p + "1.weight"), kShape); put(blob, L.inv_bb, get(p + "1.bias"), kShape);
+    put(blob, L.inv_w2, get(p + "3.weight"), kShape * kShape); put(blob, L.inv_b2, get(p + "3.bias"), kShape);
+  }
+  auto pack_edge = [&](const EdgeMlpOff& e, const std::string& p, int n2, int ld1, bool gate) {
+    const float* w1 = get(p + ".net.0.weight");
+    pack_frags(blob + e.w1r, H / 8, 2, prec, [&](int n, int k) { return k < kRbf ? w1[(size_t)n * ld1 + k] : 0.f; });
+    put(blob, e.b1, get(p + ".net.0.bias"), H);
+    put(blob, e.ln_g, get(p + ".net.1.weight"), H);
+    put(blob, e.ln_b, get(p + ".net.1.bias"), H);
+    const float* w2 = get(p + ".net.3.weight");
+    if (gate) {
+      put(blob, e.w2, w2, H);
+      put(blob, e.b2, get(p + ".net.3.bias"), 1);
+    } else {
+      pack_frags(blob + e.w2, n2 / 8, H / 16, prec, [&](int n, int k) { return w2[(size_t)n * H + k]; });
+      put(blob, e.b2, get(p + ".net.3.bias"), n2);
+    }
+  };
+  pack_edge(L.gate, "refine_net.edge_pred_layer", 0, kRbf, true);
+  {  // head: v_inference
+    const float* w1 = get("v_inference.0.weight");
+    const float* w2 = get("v_inference.2.weight");
+    pack_frags(blob + L.head.w1, H / 8, H / 16, prec, [&](int n, int k) { return w1[(size_t)n * H + k]; });
+    put(blob, L.head.b1, get("v_inference.0.bias"), H);
+    pack_frags(blob + L.head.w2, 2, H / 16, prec, [&](int n, int k) { return n < C ? w2[(size_t)n * H + k] : 0.f; });
+    put(blob, L.head.b2, get("v_inference.2.bias"), C);
+  }
+  for (int l = 0; l < d.layers; ++l) {
+    const LayerOff& y = L.layer[l];
+    const std::string b = "refine_net.base_block." + std::to_string(l);
+    const std::string x2h = b + ".x2h_layers.0.", h2x = b + ".h2x_layers.0.";
+    pack_edge(y.hk, x2h + "hk_func", H, KV, false);
+    pack_edge(y.hv, x2h + "hv_func", H, KV, false);
+    pack_edge(y.xk, h2x + "xk_func", H, KV, false);
+    pack_edge(y.xv, h2x + "xv_func", kHeads, KV, false);
+    // node-level projections of the two edge MLPs' first Linear + the query MLP
+    auto pack_pre = [&](const NodeMlpOff& n, const std::string& kf, const std::string& vf, const std::string& qf) {
+      const float* wk = get(kf + ".net.0.weight"); const float* bk = get(kf + ".net.0.bias");
+      const float* wv = get(vf + ".net.0.weight"); const float* bv = get(vf + ".net.0.bias");
+      const float* wq = get(qf + ".net.0.weight"); const float* bq = get(qf + ".net.0.bias");
+      auto W = [&](int n_, int k) -> float {
+        const int blk = n_ / H, r = n_ % H;
+        if (blk == 4) return k < H ? wq[(size_t)r * H + k] : 0.f;
+        const float* w = blk < 2 ? wk : wv;
+        if ((blk & 1) == 0)   // A: dst part + shape part
+          return k < H ? w[(size_t)r * KV + kRbf + k] : w[(size_t)r * KV + kRbf + 2 * H + (k - H)];
+        return k < H ? w[(size_t)r * KV + kRbf + H + k] : 0.f;   // B: src part
+      };
+      pack_frags(blob + n.w1, 5 * H / 8, (H + kShape) / 16, prec, W);
+      float* b1 = reinterpret_cast<float*>(blob + n.b1);
+      for (int r = 0; r < H; ++r) { b1[r] = bk[r]; b1[2 * H + r] = bv[r]; b1[4 * H + r] = bq[r]; }
+      put(blob, n.ln_g, get(qf + ".net.1.weight"), H);
+      put(blob, n.ln_b, get(qf + ".net.1.bias"), H);
+      const float* w2 = get(qf + ".net.3.weight");
+      pack_frags(blob + n.w2, H / 8, H / 16, prec, [&](int n_, int k) { return w2[(size_t)n_ * H + k]; });
+      put(blob, n.b2, get(qf + ".net.3.bias"), H);
+    };
+    pack_pre(y.x2h_pre, x2h + "hk_func", x2h + "hv_func", x2h + "hq_func");
+    pack_pre(y.h2x_pre, h2x + "xk_func", h2x + "xv_func", h2x + "xq_func");
+    {
+      const std::string p = x2h + "node_output";
+      const float* w1 = get(p + ".net.0.weight");
+      const float* w2 = get(p + ".net.3.weight");
+      pack_frags(blob + y.node_out.w1, H / 8, 2 * H / 16, prec, [&](int n, int k) { return w1[(size_t)n * 2 * H + k]; });
+      put(blob, y.node_out.b1, get(p + ".net.0.bias"), H);
+      put(blob, y.node_out.ln_g, get(p + ".net.1.weight"), H);
+      put(blob, y.node_out.ln_b, get(p + ".net.1.bias"), H);
+      pack_frags(blob + y.node_out.w2, H / 8, H / 16, prec, [&](int n, int k) { return w2[(size_t)n * H + k]; });
+      put(blob, y.node_out.b2, get(p + ".net.3.bias"), H);
+    }
+    put(blob, y.vn_feat, get(h2x + "shape_linear.map_to_feat.weight"), kHeads * kVnIn);
+    put(blob, y.vn_dir, get(h2x + "shape_linear.map_to_dir.weight"), kHeads * kVnIn);
+  }
+  return 0;
+}
+
+}  // namespace smb
+
+extern "C" {
+
+int smb_abi_version(void) { return SMB_ABI_VERSION; }
+const char* smb_last_error_string(void) { return smb::g_err; }
+
+int smb_param_count(const smb_model_dims* dims) {
+  if (!dims) return SMB_E_BADARG;
+  int rc = smb::check_dims(*dims);
+  if (rc) return rc;
+  return (int)smb::param_names(*dims).size();
+}
+const char* smb_param_name(const smb_model_dims* dims, int i) {
+  if (!dims || smb::check_dims(*dims)) return nullptr;
+  const auto& v = smb::param_names(*dims);
+  if (i < 0 || i >= (int)v.size()) return nullptr;
+  return v[i].c_str();
+}
+size_t smb_packed_weights_bytes(const smb_model_dims* dims) {
+  if (!dims || smb::check_dims(*dims)) return 0;
+  return smb::build_layout(*dims).total;
+}
+int smb_pack_weights(const smb_model_dims* dims, const float* const* host_params, int n_params, void* packed_host,
+                     size_t packed_bytes) {
+  if (!dims || !host_params || !packed_host) { smb::set_error_msg("smb_pack_weights: null argument"); return SMB_E_BADARG; }
+  int rc = smb::check_dims(*dims);
+  if (rc) return rc;
+  if (n_params != (int)smb::param_names(*dims).size()) { smb::set_error_msg("smb_pack_weights: wrong parameter count"); return SMB_E_BADARG; }
+  for (int i = 0; i < n_params; ++i)
+    if (!host_params[i]) { smb::set_error_msg("smb_pack_weights: null parameter pointer"); return SMB_E_BADARG; }
+  if (packed_bytes < smb::build_layout(*dims).total) { smb::set_error_msg("smb_pack_weights: output buffer too small"); return SMB_E_BADARG; }
+  return smb::pack_impl(*dims, host_params, reinterpret_cast<uint8_t*>(packed_host));
+}
+size_t smb_workspace_bytes(const smb_model_dims* dims, int32_t n_atoms, int32_t n_mols) {
+  if (!dims || smb::check_dims(*dims)) return 0;
+  return smb::build_workspace(*dims, n_atoms, n_mols).total;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Internal kernel argument blocks and launchers (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "smb_layout.h"
+
+namespace smb {
+
+struct PrepArgs {
+  int n_mols;
+  const int* t;            // [B]
+  const float* shape;      // [B,32,3]
+  const float *time_freq, *time_w1, *time_b1, *time_w2, *time_b2;
+  const float *inv_w1, *inv_b1, *inv_g, *inv_bb, *inv_w2, *inv_b2;
+  float* tau;              // [B,8]
+  float* inv;              // [B,32]
+};
+
+struct EmbedArgs {
+  int n_atoms, H, classes;
+  const int* v;
+  const int* atom_mol;
+  const float* tau;
+  const float* emb_wT;
+  const float* emb_b;
+  float* h;
+  float* h0;   // optional copy
+};
+
+struct BnArgs {
+  int training, n_atoms, rows;
+  const float* partial;   // [rows][32]
+  const float* weight;
+  const float* bias;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float* param;           // [32] scale | shift
+};
+
+struct PosteriorArgs {
+  int n_atoms, classes;
+  const int* atom_mol;
+  const int* t;
+  const float* pred_pos;
+  const float* pred_v;
+  float* pos;
+  int* v;
+  const float* noise_pos;
+  const float* noise_u;
+  float* log_v0;
+  float* log_post;
+  uint64_t seed;
+  int64_t atom_offset;
+  const float *c0, *ct, *logvar, *log_a, *log_1m_a, *log_ac, *log_1m_ac;
+};
+
+// Node-level chain GEMM (smb_node_mlp.cu)
+enum NodeXMode { XMODE_H_INV = 0, XMODE_AGG_H = 1, XMODE_H = 2 };
+enum NodeAct { ACT_LN_RELU = 0, ACT_SSP = 1 };
+struct NodeArgs {
+  int n_atoms;
+  int x_mode, act;
+  int n_pass;              // number of leading stage-1 columns written to out1 (multiple of 64)
+  int n2;                  // stage-2 outputs (multiple of 8), n2_valid of them stored
+  int n2_valid;
+  const float* xa;         // first input  [N][H]   (h, or agg for XMODE_AGG_H)
+  const float* xb;         // second input: inv [B][32] (H_INV) or h [N][H] (AGG_H)
+  const int* atom_mol;
+  const void* w1; const float* b1;
+  const float *ln_g, *ln_b;
+  const void* w2; const float* b2;
+  const float* residual;   // optional [N][n2]
+  float* out1;             // [N][n_pass]
+  float* out2;             // [N][n2_valid]
+};
+int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);
+
+// Edge kernels (smb_edge_attn.cu)
+enum EdgeRole { ROLE_GATE = 0, ROLE_K = 1, ROLE_V = 2, ROLE_XV = 3 };
+struct EdgeArgs {
+  int n_mols, n_max, k;
+  const int* mol_ptr;
+  const float* x;          // [N][3] current coordinates
+  const int* nbr;          // [N][k+1]
+  const int* deg;          // [N]
+  const float* ab;         // [N][4H]; columns [col_a, col_a+H) = dst part, [col_b, col_b+H) = src part
+  int col_a, col_b;
+  const float* q;          // [N][H]           (ROLE_K)
+  const float* ew_in;      // [N][k+1]         (ROLE_K: folded into alpha)
+  float* ew_out;           // [N][k+1]         (ROLE_GATE)
+  float* alpha;            // [N][k+1][16]     (ROLE_K out; ROLE_V / ROLE_XV in)
+  float* agg;              // [N][H]           (ROLE_V out)
+  // ROLE_XV
+  const float* shape;      // [B][32][3]
+  const float *vn_feat, *vn_dir;   // [16][49]
+  float* vn;               // [N][kVnRow]
+  float* bn_partial;       // [gridDim.x*warps][32]
+  // weights
+  const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
+};
+int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* grid_out, cudaStream_t st);
+
+int launch_prep(const PrepArgs& a, cudaStream_t st);
+int launch_knn(const float* x, const int* mol_ptr, int n_mols, int k, int* nbr, int* deg, cudaStream_t st);
+int launch_embed(const EmbedArgs& a, cudaStream_t st);
+int launch_bn_final(const BnArgs& a, cudaStream_t st);
+int launch_vn_apply(const float* vn, const float* bn_param, float* x, float* x_out, int n_atoms, cudaStream_t st);
+int launch_posterior(const PosteriorArgs& a, cudaStream_t st);
+int launch_decrement_t(int* t, int n, cudaStream_t st);
+
+}  // namespace smb

@@ -1,0 +1,94 @@
+// Packed-weight and workspace layout shared by the host packer and the kernel launchers.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/shapemol_b200.h"
+
+namespace smb {
+
+constexpr int kHeads = 16;
+constexpr int kShape = SMB_SHAPE_DIM;       // shape_dim = shape_latent_dim = 32
+constexpr int kRbf = SMB_N_RBF;             // 20 (padded to K=32 for the tensor-core first Linear)
+constexpr int kVnIn = 1 + kHeads + kShape;  // 49 channels into shape_linear
+constexpr int kVnStride = 49;               // row stride of the VN weights in the blob
+constexpr int kMaxLayers = 16;
+
+// Edge MLP (Linear(2H+20+32 -> H) -> LN -> ReLU -> Linear(H -> N2)) with its first Linear split:
+//   W1 [r | h_dst | h_src | inv_dst]: the r part lives here (tensor-core B fragments, K padded to
+//   32); the h_dst/inv part and the h_src part are node-level projections (NodeMlp below).
+struct EdgeMlpOff {
+  size_t w1r;    // B fragments [H/8][2][32] (uint4 hi/lo  or  uint2 hi)
+  size_t b1;     // [H] fp32 (only used by the gate MLP: the other MLPs fold b1 into the A projection)
+  size_t ln_g;   // [H]
+  size_t ln_b;   // [H]
+  size_t w2;     // B fragments [N2/8][H/16][32]   (gate: fp32 [H] vector)
+  size_t b2;     // [N2] fp32
+};
+
+// Node-level chain: Y1 = X W1^T + b1 ; first n_pass columns are written out as they are, the last H
+// columns go through LN/ReLU (or shifted softplus) and a second Linear.
+struct NodeMlpOff {
+  size_t w1;     // B fragments [N1/8][K1/16][32]
+  size_t b1;     // [N1]
+  size_t ln_g;   // [H]
+  size_t ln_b;   // [H]
+  size_t w2;     // B fragments [N2/8][H/16][32]
+  size_t b2;     // [N2]
+};
+
+struct LayerOff {
+  EdgeMlpOff hk, hv, xk, xv;
+  NodeMlpOff x2h_pre;   // X=[h|inv] (K1=H+32) -> [A_hk|B_hk|A_hv|B_hv | hq hidden] -> Q_h
+  NodeMlpOff node_out;  // X=[agg|h] (K1=2H)  -> hidden -> h' (+h residual)
+  NodeMlpOff h2x_pre;   // X=[h'|inv]         -> [A_xk|B_xk|A_xv|B_xv | xq hidden] -> Q_x
+  size_t vn_feat;       // [16][49] fp32
+  size_t vn_dir;        // [16][49] fp32
+};
+
+struct ModelLayout {
+  size_t total;
+  size_t time_freq;     // [time_dim/2]
+  size_t time_w1, time_b1, time_w2, time_b2;
+  size_t emb_wT;        // [classes+time_dim][H] (transposed ligand_atom_emb.weight)
+  size_t emb_b;         // [H]
+  size_t inv_w1, inv_b1, inv_g, inv_bb, inv_w2, inv_b2;   // invariant_shape_layer MLP 32->32->32
+  EdgeMlpOff gate;      // edge_pred_layer
+  NodeMlpOff head;      // v_inference: X=h (K1=H) -> H -> ssp -> classes (padded to 16)
+  LayerOff layer[kMaxLayers];
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline size_t frag_bytes(const smb_model_dims& d) { return d.precision == SMB_PREC_BF16X3 ? 16 : 8; }
+
+ModelLayout build_layout(const smb_model_dims& d);
+const std::vector<std::string>& param_names(const smb_model_dims& d);
+int check_dims(const smb_model_dims& d);
+
+struct Workspace {
+  size_t total;
+  size_t tau;       // [B][8]
+  size_t inv;       // [B][32]
+  size_t nbr;       // [N][k+1] int32
+  size_t deg;       // [N] int32
+  size_t ew;        // [N][k+1]
+  size_t alpha;     // [N][k+1][16]
+  size_t x;         // [N][3]
+  size_t h_a;       // [N][H]
+  size_t h_b;       // [N][H]
+  size_t ab;        // [N][4H]
+  size_t q;         // [N][H]
+  size_t agg;       // [N][H]
+  size_t vn;        // [N][100]  (o_mean 3 | p 48 | d 48 | pad)
+  size_t bn_part;   // [bn_part_rows][32]
+  size_t bn_param;  // [32] scale | shift
+  int bn_part_rows;
+};
+constexpr int kVnRow = 100;
+constexpr int kEdgeMaxCtas = 148 * 2;
+constexpr int kEdgeWarps = 8;
+Workspace build_workspace(const smb_model_dims& d, int n_atoms, int n_mols);
+
+}  // namespace smb

@@ -1,0 +1,232 @@
+"""Drop-in ScorePosNet3D (reference models/molopt_score_model.py:169-697).
+
+Same constructor, attributes, state_dict keys, forward() and sample_diffusion() signatures and return
+values as the reference; the arithmetic runs in libshapemol_b200 (hand-written sm_100a kernels) through
+shapemol_b200.engine.  No eager / CPU fallback: unsupported options raise.
+
+Extensions (attributes, not part of the reference API):
+    model.smb_precision   'bf16x3' (default; fp32-parity mode) or 'bf16' (throughput mode)
+    model.smb_noise       'torch' (default; the reference's RNG draw order) or 'philox' (in-kernel)
+    model.smb_keep_traj   True (default; per-step trajectories as in the reference) or False
+    model.smb_use_graph   True (default)
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from tqdm.auto import tqdm
+
+from models.common import ShiftedSoftplus
+from models.diffusion import get_beta_schedule
+from models.uni_transformer import UniTransformerO2TwoUpdateGeneral
+
+
+def get_refine_net(refine_net_type, config):
+    """reference :13-42"""
+    if refine_net_type != 'uni_o2':
+        raise ValueError(refine_net_type)
+    return UniTransformerO2TwoUpdateGeneral(
+        num_blocks=config.num_blocks, num_layers=config.num_layers, hidden_dim=config.hidden_dim,
+        shape_dim=config.shape_dim, shape_latent_dim=config.shape_latent_dim, n_heads=config.n_heads, k=config.knn,
+        edge_feat_dim=config.edge_feat_dim, num_r_gaussian=config.num_r_gaussian, num_node_types=config.num_node_types,
+        act_fn=config.act_fn, norm=config.norm, cutoff_mode=config.cutoff_mode, ew_net_type=config.ew_net_type,
+        topo_emb_type=config.topo_emb_type, r_feat_mode=config.r_feat_mode, num_x2h=config.num_x2h, num_h2x=config.num_h2x,
+        r_max=config.r_max, x2h_out_fc=config.x2h_out_fc, atom_enc_mode=config.atom_enc_mode, shape_type=config.shape_type,
+        sync_twoup=config.sync_twoup)
+
+
+def to_torch_const(x):
+    return nn.Parameter(torch.from_numpy(x).float(), requires_grad=False)
+
+
+def log_1_min_a(a):
+    return np.log(1 - np.exp(a) + 1e-40)
+
+
+def log_sample_categorical(logits):
+    """reference :98-104 (used by scripts/sample_diffusion.py:93 for the initial atom types)."""
+    uniform = torch.rand_like(logits)
+    gumbel_noise = -torch.log(-torch.log(uniform + 1e-30) + 1e-30)
+    return (gumbel_noise + logits).argmax(dim=-1)
+
+
+def index_to_log_onehot(x, num_classes):
+    """reference :64-68"""
+    return torch.log(F.one_hot(x, num_classes).float().clamp(min=1e-30))
+
+
+def extract(coef, t, batch):
+    return coef[t][batch].unsqueeze(-1)
+
+
+class SinusoidalPosEmb(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+
+class ScorePosNet3D(nn.Module):
+
+    def __init__(self, config, ligand_atom_feature_dim):
+        super().__init__()
+        self.config = config
+        self.denoise_type = config.denoise_type
+        self.model_mean_type = config.model_mean_type
+        self.loss_v_weight = config.loss_v_weight
+        self.loss_weight_type = config.loss_weight_type
+        self.v_mode = config.v_mode
+        self.v_net_type = getattr(config, 'v_net_type', 'mlp')
+        self.sample_time_method = config.sample_time_method
+        self.loss_pos_type = config.loss_pos_type
+        if self.v_mode != 'uniform' or self.v_net_type != 'mlp' or self.model_mean_type != 'C0':
+            raise NotImplementedError('shapemol_b200 builds v_mode=uniform, v_net_type=mlp, model_mean_type=C0 only')
+        if config.time_emb_dim != 8:
+            raise NotImplementedError('time_emb_dim must be 8')
+
+        # ---- variance schedules, fp64 numpy -> fp32 parameters (reference :188-234) ----
+        betas = get_beta_schedule(num_diffusion_timesteps=config.num_diffusion_timesteps, **config.schedule_pos)
+        alphas = 1. - betas
+        alphas_cumprod = np.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = np.append(1., alphas_cumprod[:-1])
+        if self.loss_weight_type == 'noise_level':
+            snr = alphas_cumprod / (1 - alphas_cumprod)
+            self.loss_pos_step_weight = to_torch_const(np.clip(config.loss_pos_min_weight + snr, None, config.loss_pos_max_weight))
+        self.betas = to_torch_const(betas)
+        self.num_timesteps = self.betas.size(0)
+        self.alphas_cumprod = to_torch_const(alphas_cumprod)
+        self.alphas_cumprod_prev = to_torch_const(alphas_cumprod_prev)
+        self.sqrt_alphas_cumprod = to_torch_const(np.sqrt(alphas_cumprod))
+        self.sqrt_one_minus_alphas_cumprod = to_torch_const(np.sqrt(1. - alphas_cumprod))
+        self.sqrt_recip_alphas_cumprod = to_torch_const(np.sqrt(1. / alphas_cumprod))
+        self.sqrt_recipm1_alphas_cumprod = to_torch_const(np.sqrt(1. / alphas_cumprod - 1))
+        posterior_variance = betas * (1. - alphas_cumprod_prev) / (1. - alphas_cumprod)
+        self.posterior_mean_c0_coef = to_torch_const(betas * np.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod))
+        self.posterior_mean_ct_coef = to_torch_const((1. - alphas_cumprod_prev) * np.sqrt(alphas) / (1. - alphas_cumprod))
+        self.posterior_var = to_torch_const(posterior_variance)
+        # entry 0 replaced by entry 1, taken from the fp32 parameter like the reference (:220)
+        self.posterior_logvar = to_torch_const(np.log(np.append(self.posterior_var[1], self.posterior_var[1:])))
+        betas_v = get_beta_schedule(num_diffusion_timesteps=config.num_diffusion_timesteps, **config.schedule_v)
+        log_alphas_v = np.log(1. - betas_v)
+        log_alphas_cumprod_v = np.cumsum(log_alphas_v)
+        self.log_alphas_v = to_torch_const(log_alphas_v)
+        self.log_one_minus_alphas_v = to_torch_const(log_1_min_a(log_alphas_v))
+        self.log_alphas_cumprod_v = to_torch_const(log_alphas_cumprod_v)
+        self.log_one_minus_alphas_cumprod_v = to_torch_const(log_1_min_a(log_alphas_cumprod_v))
+
+        # ---- network parameters ----
+        self.hidden_dim = config.hidden_dim
+        self.num_classes = ligand_atom_feature_dim
+        self.center_pos_mode = config.center_pos_mode
+        self.time_emb_dim = config.time_emb_dim
+        self.time_emb = nn.Sequential(SinusoidalPosEmb(self.time_emb_dim), nn.Linear(self.time_emb_dim, self.time_emb_dim * 2),
+                                      nn.SiLU(), nn.Linear(self.time_emb_dim * 2, self.time_emb_dim))
+        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim + self.time_emb_dim, self.hidden_dim)
+        self.refine_net_type = config.model_type
+        self.refine_net = get_refine_net(self.refine_net_type, config)
+        self.v_inference = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), ShiftedSoftplus(),
+                                         nn.Linear(self.hidden_dim, ligand_atom_feature_dim))
+        self.cond_mask_prob = config.cond_mask_prob
+
+        # ---- B200 engine (lazy: the CUDA library is loaded at the first forward) ----
+        self.smb_precision = 'bf16x3'
+        self.smb_noise = 'torch'
+        self.smb_keep_traj = True
+        self.smb_use_graph = True
+        self.smb_seed = 0
+        self._smb_engine = None
+        self._smb_batch_cache = None
+
+    # ------------------------------------------------------------------------------------------
+    def _engine(self):
+        from shapemol_b200.engine import DenoiseEngine
+        if self._smb_engine is None:
+            object.__setattr__(self, '_smb_engine', DenoiseEngine(self, self.smb_precision))
+        if self._smb_engine.precision != self.smb_precision:
+            self._smb_engine.set_precision(self.smb_precision)
+        return self._smb_engine
+
+    def _batch_desc(self, batch_ligand):
+        from shapemol_b200.engine import BatchDesc
+        key = (batch_ligand.data_ptr(), batch_ligand._version, batch_ligand.numel(), str(batch_ligand.device))
+        c = self._smb_batch_cache
+        if c is None or c[0] != key:
+            c = (key, BatchDesc(batch_ligand))
+            object.__setattr__(self, '_smb_batch_cache', c)
+        return c[1]
+
+    @torch.no_grad()
+    def forward(self, ligand_pos_perturbed, ligand_v_perturbed, batch_ligand, ligand_shape, time_step=None, return_all=False):
+        """f(x0, v0 | xt, vt) -- reference :286-320 (inference only: the kernels have no backward)."""
+        eng = self._engine()
+        bd = self._batch_desc(batch_ligand)
+        dev = ligand_pos_perturbed.device
+        N, B = bd.n_atoms, bd.n_mols
+        pos = ligand_pos_perturbed.detach().to(torch.float32).contiguous()
+        v = ligand_v_perturbed.detach().to(torch.int32).contiguous()
+        shape = ligand_shape.detach().to(torch.float32).reshape(B, -1, 3).contiguous()
+        t = time_step.detach().to(torch.int32).contiguous()
+        pred_pos = torch.empty(N, 3, device=dev)
+        pred_h = torch.empty(N, self.hidden_dim, device=dev)
+        pred_v = torch.empty(N, self.num_classes, device=dev)
+        h0 = torch.empty(N, self.hidden_dim, device=dev) if return_all else None
+        eng.forward(pos, v, bd, shape, t, pred_pos, pred_h, pred_v, h0=h0)
+        preds = {'pred_ligand_pos': pred_pos, 'pred_ligand_h': pred_h, 'pred_ligand_v': pred_v}
+        if return_all:
+            # num_blocks == 1: all_x = [x_in, x_out], all_h = [h0, h_out]  (uni_transformer.py:489-539)
+            v0 = torch.empty(N, self.num_classes, device=dev)
+            eng.type_head(h0, bd, v0)
+            preds.update({'layer_pred_ligand_pos': [pos, pred_pos], 'layer_pred_ligand_v': [v0, pred_v]})
+        return preds
+
+    # ---- categorical posterior helpers kept for API compatibility (torch ops, not on the hot path) ----
+    def q_v_pred_one_timestep(self, log_vt_1, t, batch):
+        a, b = extract(self.log_alphas_v, t, batch), extract(self.log_one_minus_alphas_v, t, batch)
+        return torch.logaddexp(log_vt_1 + a, b - np.log(self.num_classes))
+
+    def q_v_pred(self, log_v0, t, batch):
+        a, b = extract(self.log_alphas_cumprod_v, t, batch), extract(self.log_one_minus_alphas_cumprod_v, t, batch)
+        return torch.logaddexp(log_v0 + a, b - np.log(self.num_classes))
+
+    def q_v_posterior(self, log_v0, log_vt, t, batch):
+        tm1 = torch.where(t - 1 < 0, torch.zeros_like(t), t - 1)
+        un = self.q_v_pred(log_v0, tm1, batch) + self.q_v_pred_one_timestep(log_vt, t, batch)
+        return un - torch.logsumexp(un, dim=-1, keepdim=True)
+
+    def q_pos_posterior(self, x0, xt, t, batch):
+        return extract(self.posterior_mean_c0_coef, t, batch) * x0 + extract(self.posterior_mean_ct_coef, t, batch) * xt
+
+    def get_diffusion_loss(self, *args, **kwargs):
+        raise NotImplementedError('training is outside the shapemol_b200 hot path (SURVEY 2 #10)')
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_diffusion(self, init_ligand_pos, init_ligand_v, batch_ligand, ligand_shape, threshold_type=None,
+                         threshold_args=None, num_steps=None, center_pos_mode=None, use_grad=False, grad_lr=1,
+                         shape_AE=None, use_mesh_data=None, use_pointcloud_data=None, grad_step=500,
+                         guide_stren=0, bounds=None):
+        """Reverse diffusion -- reference :533-697, default (no-guidance) branch."""
+        from shapemol_b200.engine import Sampler
+        if num_steps is None:
+            num_steps = self.num_timesteps
+        print('sample center pos mode: ', center_pos_mode)
+        if self.cond_mask_prob == 0:
+            assert guide_stren == 0
+        if use_mesh_data is not None or use_pointcloud_data is not None or (self.cond_mask_prob > 0 and guide_stren > 0.0):
+            raise NotImplementedError('shape guidance / classifier-free guidance branches are not built (SURVEY 8f-1)')
+        if center_pos_mode not in (None, 'none'):
+            raise NotImplementedError("center_pos_mode=%r is not built (shipped configs use 'none')" % (center_pos_mode,))
+        eng = self._engine()
+        sampler = Sampler(eng, init_ligand_pos, init_ligand_v, batch_ligand, ligand_shape, num_steps=num_steps,
+                          noise=self.smb_noise, seed=self.smb_seed, keep_traj=self.smb_keep_traj, use_graph=self.smb_use_graph)
+        pos, v = sampler.run(progress=lambda it: tqdm(it, desc='sampling', total=num_steps))
+        out = {'pos': pos, 'v': v.to(torch.long), 'pos_traj': [], 'pos_cond_traj': [], 'pos_uncond_traj': [], 'v_traj': [],
+               'v_cond_traj': [], 'v_uncond_traj': [], 'v0_traj': [], 'vt_traj': []}
+        if self.smb_keep_traj:
+            tr = sampler.traj
+            out['pos_traj'] = list(tr['pos'].cpu().unbind(0))                      # CPU tensors, as the reference (:680)
+            out['v_traj'] = list(tr['v'].cpu().to(torch.long).unbind(0))
+            out['v0_traj'] = list(tr['v0'].cpu().unbind(0))
+            out['vt_traj'] = list(tr['vt'].cpu().unbind(0))
+            out['pos_cond_traj'] = list(tr['pos_cond'].unbind(0))                  # device tensors (:645-646)
+            out['v_cond_traj'] = list(tr['v_cond'].unbind(0))
+        return out

@@ -1,0 +1,241 @@
+"""Host-side driver of the CUDA library: packs weights, owns workspaces, runs the step loop.
+
+PyTorch is plumbing here (device memory, streams, the RNG stream the reference uses); all arithmetic
+of the hot path is enqueued through the C ABI (shapemol_b200/_lib.py).  There is no eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+SCHEDULE_TABLES = ('posterior_mean_c0_coef', 'posterior_mean_ct_coef', 'posterior_logvar', 'log_alphas_v',
+                   'log_one_minus_alphas_v', 'log_alphas_cumprod_v', 'log_one_minus_alphas_cumprod_v')
+
+
+class BatchDesc:
+    """Ragged batch descriptor (mol_ptr / atom_mol on the device) built once per batch."""
+
+    def __init__(self, batch_ligand, n_mols=None):
+        dev = batch_ligand.device
+        if dev.type != 'cuda':
+            raise _lib.SmbError('shapemol_b200 runs on CUDA devices only (got %s); there is no CPU path' % dev)
+        self.device = dev
+        self.n_atoms = int(batch_ligand.numel())
+        if n_mols is None:
+            n_mols = int(batch_ligand.max().item()) + 1 if self.n_atoms else 0   # same sync as the reference (:290)
+        self.n_mols = n_mols
+        counts = torch.bincount(batch_ligand, minlength=max(n_mols, 1))[:max(n_mols, 1)]
+        self.max_atoms = int(counts.max().item()) if self.n_atoms else 0
+        if self.max_atoms > _lib.SMB_MAX_ATOMS_PER_MOL:
+            raise _lib.SmbError('molecule with %d atoms exceeds SMB_MAX_ATOMS_PER_MOL=%d' % (self.max_atoms, _lib.SMB_MAX_ATOMS_PER_MOL))
+        ptr = torch.zeros(n_mols + 1, dtype=torch.int32, device=dev)
+        if n_mols:
+            ptr[1:] = torch.cumsum(counts[:n_mols], 0).to(torch.int32)
+        self.mol_ptr = ptr
+        self.atom_mol = batch_ligand.to(torch.int32).contiguous()
+        if self.n_atoms > 1 and bool((self.atom_mol[1:] < self.atom_mol[:-1]).any().item()):
+            raise _lib.SmbError('batch_ligand must be sorted (atoms of a molecule contiguous)')
+        self.c = _lib.Batch(self.n_atoms, self.n_mols, self.max_atoms, self.mol_ptr.data_ptr(), self.atom_mol.data_ptr())
+
+
+class DenoiseEngine:
+    """One engine per ScorePosNet3D module instance."""
+
+    def __init__(self, module, precision='bf16x3'):
+        self.module = module
+        self.lib = _lib.load()
+        self.set_precision(precision)
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+        self._names = None
+
+    # ---- configuration ---------------------------------------------------------------------
+    def set_precision(self, precision):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError('precision must be one of %s' % sorted(_lib.PRECISIONS))
+        self.precision = precision
+        self._packed_key = None
+
+    def dims(self):
+        m = self.module
+        rn = m.refine_net
+        return _lib.ModelDims(hidden=m.hidden_dim, heads=rn.n_heads, layers=rn.num_layers, k=rn.k, classes=m.num_classes,
+                              time_dim=m.time_emb_dim, timesteps=m.num_timesteps, precision=_lib.PRECISIONS[self.precision])
+
+    # ---- weights ---------------------------------------------------------------------------
+    def _param_names(self, dims):
+        if self._names is None:
+            n = self.lib.smb_param_count(C.byref(dims))
+            if n <= 0:
+                _lib.check(n if n < 0 else -1, 'smb_param_count')
+            self._names = [self.lib.smb_param_name(C.byref(dims), i).decode() for i in range(n)]
+        return self._names
+
+    def packed_weights(self, device):
+        dims = self.dims()
+        names = self._param_names(dims)
+        sd = self.module.state_dict(keep_vars=True)
+        key = (self.precision, str(device)) + tuple((sd[n].data_ptr(), sd[n]._version) for n in names)
+        if key != self._packed_key:
+            host = [sd[n].detach().to('cpu', torch.float32).contiguous() for n in names]
+            arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+            nbytes = self.lib.smb_packed_weights_bytes(C.byref(dims))
+            blob = torch.empty(nbytes, dtype=torch.uint8)
+            _lib.check(self.lib.smb_pack_weights(C.byref(dims), arr, len(host), blob.data_ptr(), nbytes), 'smb_pack_weights')
+            self._packed = blob.to(device)
+            self._packed_key = key
+        return self._packed
+
+    def workspace(self, dims, n_atoms, n_mols, device):
+        need = self.lib.smb_workspace_bytes(C.byref(dims), n_atoms, n_mols)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _bn_layers(self):
+        return [blk.h2x_layers[0].shape_linear.batchnorm.bn for blk in self.module.refine_net.base_block]
+
+    # ---- one network evaluation --------------------------------------------------------------
+    def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None):
+        dims = self.dims()
+        dev = pos.device
+        blob = self.packed_weights(dev)
+        ws = self.workspace(dims, bd.n_atoms, bd.n_mols, dev)
+        io = _lib.ForwardIO()
+        io.pos, io.v, io.shape, io.t = pos.data_ptr(), v_i32.data_ptr(), shape.data_ptr(), t_i32.data_ptr()
+        io.pred_pos, io.pred_h, io.pred_v = pred_pos.data_ptr(), pred_h.data_ptr(), pred_v.data_ptr()
+        io.h0, io.nbr = _lib.ptr(h0), _lib.ptr(nbr)
+        for l, bn in enumerate(self._bn_layers()):
+            for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var):
+                if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.SmbError('BatchNorm tensors must be contiguous fp32 on %s' % dev)
+            io.bn_weight[l], io.bn_bias[l] = bn.weight.data_ptr(), bn.bias.data_ptr()
+            io.bn_running_mean[l], io.bn_running_var[l] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            io.bn_num_batches_tracked[l] = bn.num_batches_tracked.data_ptr()
+        io.training = int(self.module.training if training is None else training)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.smb_forward(C.byref(dims), blob.data_ptr(), C.byref(bd.c), C.byref(io), ws.data_ptr(), ws.numel(), stream),
+                   'smb_forward')
+
+    def type_head(self, h, bd, logits):
+        dims = self.dims()
+        blob = self.packed_weights(h.device)
+        stream = torch.cuda.current_stream(h.device).cuda_stream
+        _lib.check(self.lib.smb_type_head(C.byref(dims), blob.data_ptr(), C.byref(bd.c), h.data_ptr(), logits.data_ptr(), stream),
+                   'smb_type_head')
+
+    # ---- one reverse-diffusion update ----------------------------------------------------------
+    def posterior(self, bd, pred_pos, pred_v, t_i32, pos, v_i32, noise_pos=None, noise_u=None, log_v0=None, log_post=None,
+                  seed=0, atom_offset=0):
+        dims = self.dims()
+        m = self.module
+        io = _lib.PosteriorIO()
+        io.pred_pos, io.pred_v, io.t, io.pos, io.v = pred_pos.data_ptr(), pred_v.data_ptr(), t_i32.data_ptr(), pos.data_ptr(), v_i32.data_ptr()
+        io.noise_pos, io.noise_u, io.log_v0, io.log_post = _lib.ptr(noise_pos), _lib.ptr(noise_u), _lib.ptr(log_v0), _lib.ptr(log_post)
+        io.seed, io.atom_offset = int(seed) & (2 ** 64 - 1), int(atom_offset)
+        for name in SCHEDULE_TABLES:
+            tab = getattr(m, name)
+            if tab.device != pos.device:
+                raise _lib.SmbError('schedule table %s is not on %s' % (name, pos.device))
+            setattr(io, name, tab.data_ptr())
+        stream = torch.cuda.current_stream(pos.device).cuda_stream
+        _lib.check(self.lib.smb_posterior_step(C.byref(dims), C.byref(bd.c), C.byref(io), stream), 'smb_posterior_step')
+
+    def decrement_t(self, t_i32):
+        stream = torch.cuda.current_stream(t_i32.device).cuda_stream
+        _lib.check(self.lib.smb_decrement_t(t_i32.data_ptr(), t_i32.numel(), stream), 'smb_decrement_t')
+
+    def knn_graph(self, x, bd, k):
+        nbr = torch.empty(bd.n_atoms, k + 1, dtype=torch.int32, device=x.device)
+        deg = torch.empty(bd.n_atoms, dtype=torch.int32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self.lib.smb_knn_graph(x.data_ptr(), C.byref(bd.c), k, nbr.data_ptr(), deg.data_ptr(), stream), 'smb_knn_graph')
+        return nbr, deg
+
+
+class Sampler:
+    """Reverse-diffusion loop (ScorePosNet3D.sample_diffusion default branch) with persistent device
+    state, no host synchronisation inside the loop and the step captured in a CUDA graph.
+
+    noise = 'torch'  : per step torch.randn_like(pos) then torch.rand(N, C) from the device's default
+                       generator -- the reference's draw order, so torch.manual_seed(s) reproduces it;
+            'philox' : in-kernel Philox4x32 keyed by (seed, global atom index, t)   (throughput mode);
+            callable : noise(step) -> (randn [N,3], rand [N,C])                    (parity tests).
+    """
+
+    def __init__(self, engine, init_pos, init_v, batch_ligand, shape, num_steps=None, noise='torch', seed=0, atom_offset=0,
+                 keep_traj=True, use_graph=True, n_mols=None):
+        m = engine.module
+        self.e = engine
+        dev = init_pos.device
+        self.bd = BatchDesc(batch_ligand, n_mols)
+        N, B, Cn, H = self.bd.n_atoms, self.bd.n_mols, m.num_classes, m.hidden_dim
+        T = m.num_timesteps
+        self.num_steps = T if num_steps is None else int(num_steps)
+        self.pos = init_pos.detach().to(torch.float32).clone().contiguous()
+        self.v = init_v.detach().to(torch.int32).contiguous().clone()
+        self.shape = shape.detach().to(torch.float32).reshape(B, -1, 3).contiguous()
+        self.t = torch.full((max(B, 1),), T - 1, dtype=torch.int32, device=dev)
+        self.pred_pos = torch.empty(N, 3, device=dev)
+        self.pred_h = torch.empty(N, H, device=dev)
+        self.pred_v = torch.empty(N, Cn, device=dev)
+        self.noise = noise
+        self.seed, self.atom_offset = seed, atom_offset
+        self.keep_traj = keep_traj
+        self.noise_pos = torch.empty(N, 3, device=dev) if noise != 'philox' else None
+        self.noise_u = torch.empty(N, Cn, device=dev) if noise != 'philox' else None
+        self.log_v0 = torch.empty(N, Cn, device=dev) if keep_traj else None
+        self.log_post = torch.empty(N, Cn, device=dev) if keep_traj else None
+        self.use_graph = use_graph and not callable(noise)
+        self.graph = None
+        if keep_traj:
+            S = self.num_steps
+            self.traj = {k: torch.empty((S,) + tuple(s), dtype=dt, device=dev) for k, s, dt in (
+                ('pos', (N, 3), torch.float32), ('v', (N,), torch.int32), ('v0', (N, Cn), torch.float32),
+                ('vt', (N, Cn), torch.float32), ('pos_cond', (N, 3), torch.float32), ('v_cond', (N, Cn), torch.float32))}
+
+    def _step_body(self, step):
+        e = self.e
+        e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v)
+        if self.noise == 'torch':
+            self.noise_pos.normal_()     # == torch.randn_like(pos): same generator consumption
+            self.noise_u.uniform_()      # == torch.rand_like(logits)
+        elif callable(self.noise):
+            npos, nu = self.noise(step)
+            self.noise_pos.copy_(npos)
+            self.noise_u.copy_(nu)
+        e.posterior(self.bd, self.pred_pos, self.pred_v, self.t, self.pos, self.v, self.noise_pos, self.noise_u,
+                    self.log_v0, self.log_post, seed=self.seed, atom_offset=self.atom_offset)
+        e.decrement_t(self.t)
+
+    def _record(self, step):
+        tr = self.traj
+        tr['pos_cond'][step].copy_(self.pred_pos)     # posterior leaves the predictions intact
+        tr['v_cond'][step].copy_(self.pred_v)
+        tr['pos'][step].copy_(self.pos)
+        tr['v'][step].copy_(self.v)
+        tr['v0'][step].copy_(self.log_v0)
+        tr['vt'][step].copy_(self.log_post)
+
+    def run(self, progress=None):
+        steps = range(self.num_steps)
+        if progress is not None:
+            steps = progress(steps)
+        for s in steps:
+            if not self.use_graph or s == 0:
+                self._step_body(s)        # step 0 runs eagerly (it also warms up the kernels)
+            else:
+                if self.graph is None:
+                    self._capture(s)
+                self.graph.replay()
+            if self.keep_traj:
+                self._record(s)           # the trajectory slot depends on the step: outside the graph
+        return self.pos, self.v
+
+    def _capture(self, step):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body(step)
+        self.graph = g

@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path (through the C ABI / drop-in ScorePosNet3D) against
+ (1) golden fixtures produced by the unmodified reference, (2) the oracle on seeded inputs,
+ (3) size-independent properties at larger sizes.
+
+Tolerances (north_star): kNN indices bit-exact; x0 / logits within 1e-3 relative in the fp32-parity
+mode ('bf16x3'); plain bf16 is stated separately (looser bound, asserted and printed).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden, golden_weights, oracle_cfg, manifest_shapes
+from test_host_cpu import make_dropin
+
+pytestmark = pytest.mark.gpu
+
+FWD_H128 = ['k32_train', 'k32_eval', 'k8_train', 'k8_eval', 'tiny_train']
+REL_FP32 = 1e-3      # north_star tolerance, fp32-parity mode
+REL_BF16 = 3e-2      # plain bf16 operands (stated separately)
+
+
+def rel_err(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+def batch_of(sizes, dev='cuda'):
+    return torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes)).to(dev)
+
+
+def build_model(fx, precision='bf16x3', training=None):
+    m, msm = make_dropin(knn=fx['k'])
+    sd = golden_weights(fx)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    m = m.cuda()
+    m.smb_precision = precision
+    m.train(fx['training'] if training is None else training)
+    return m
+
+
+def dense_to_edges(nbr, deg, mol_ptr):
+    """Dense [N,k+1] table -> the reference's edge_index [2,E] (src = neighbour, dst = centre)."""
+    nbr, deg, mol_ptr = nbr.cpu(), deg.cpu(), mol_ptr.cpu()
+    N = nbr.shape[0]
+    sizes = mol_ptr[1:] - mol_ptr[:-1]
+    start = torch.repeat_interleave(mol_ptr[:-1], sizes)
+    mask = torch.arange(nbr.shape[1])[None, :] < deg[:, None]
+    assert bool(((nbr >= 0) == mask).all())
+    dst = torch.arange(N)[:, None].expand_as(nbr)[mask]
+    src = (nbr + start[:, None].to(nbr.dtype))[mask]
+    return torch.stack([src, dst], 0).int()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_knn_golden_tie_cases_bit_exact(cuda_lib):
+    from shapemol_b200.engine import BatchDesc, DenoiseEngine
+    m, _ = make_dropin(knn=32)
+    eng = DenoiseEngine(m)
+    for name, c in load_golden('knn_cases.pt').items():
+        n = c['x'].shape[0]
+        bd = BatchDesc(torch.zeros(n, dtype=torch.long, device='cuda'))
+        nbr, deg = eng.knn_graph(c['x'].cuda().contiguous(), bd, c['k'])
+        assert torch.equal(dense_to_edges(nbr, deg, bd.mol_ptr), c['edge_index']), name
+
+
+def test_knn_random_ragged_vs_oracle_bit_exact(cuda_lib):
+    from oracle import shapemol_oracle as orc
+    from shapemol_b200.engine import BatchDesc, DenoiseEngine
+    m, _ = make_dropin(knn=32)
+    eng = DenoiseEngine(m)
+    g = torch.Generator().manual_seed(3)
+    for k in (8, 32, 48):
+        sizes = torch.randint(1, 61, (200,), generator=g).tolist()
+        x = torch.randn(sum(sizes), 3, generator=g) * 3
+        x[5] = x[4]                                   # a duplicate point
+        x = (x * 4).round() / 4 if k == 8 else x      # quantised coordinates => many exact ties
+        bd = BatchDesc(batch_of(sizes))
+        nbr, deg = eng.knn_graph(x.cuda(), bd, k)
+        ref = orc.knn_edges(x, orc.mol_ptr_from_sizes(sizes), k)
+        assert torch.equal(dense_to_edges(nbr, deg, bd.mol_ptr), ref.int()), k
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', FWD_H128)
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_forward_matches_reference_fixture(cuda_lib, name, precision):
+    fx = load_golden('forward_%s.pt' % name)
+    m = build_model(fx, precision)
+    out = m(fx['pos'].cuda(), fx['v'].cuda(), batch_of(fx['sizes']), fx['shape'].cuda(), time_step=fx['t'].cuda())
+    torch.cuda.synchronize()
+    tol = REL_FP32 if precision == 'bf16x3' else REL_BF16
+    errs = {k: rel_err(out[k], fx[r]) for k, r in (('pred_ligand_pos', 'pred_pos'), ('pred_ligand_h', 'pred_h'), ('pred_ligand_v', 'pred_v'))}
+    print(name, precision, errs)
+    for k, e in errs.items():
+        assert e < tol, (k, e)
+    assert out['pred_ligand_pos'].shape == fx['pred_pos'].shape and out['pred_ligand_v'].shape == fx['pred_v'].shape
+    if fx['training'] and precision == 'bf16x3':
+        sd = m.state_dict()
+        for l in (0, 7):
+            p = 'refine_net.base_block.%d.h2x_layers.0.shape_linear.batchnorm.bn.' % l
+            assert torch.allclose(sd[p + 'running_mean'].cpu(), fx['bn%d_running_mean' % l], rtol=1e-3, atol=1e-5)
+            assert torch.allclose(sd[p + 'running_var'].cpu(), fx['bn%d_running_var' % l], rtol=5e-3, atol=1e-5)
+            assert int(sd[p + 'num_batches_tracked']) == 1
+
+
+def test_forward_knn_table_matches_fixture(cuda_lib):
+    from shapemol_b200.engine import BatchDesc
+    for name in ('k8_train', 'k32_train'):
+        fx = load_golden('forward_%s.pt' % name)
+        m = build_model(fx)
+        eng = m._engine()
+        bd = BatchDesc(batch_of(fx['sizes']))
+        nbr, deg = eng.knn_graph(fx['pos'].cuda(), bd, fx['k'])
+        assert torch.equal(dense_to_edges(nbr, deg, bd.mol_ptr), fx['edge_index'])
+
+
+def test_forward_return_all(cuda_lib):
+    fx = load_golden('forward_k32_eval.pt')
+    m = build_model(fx)
+    out = m(fx['pos'].cuda(), fx['v'].cuda(), batch_of(fx['sizes']), fx['shape'].cuda(), time_step=fx['t'].cuda(), return_all=True)
+    assert len(out['layer_pred_ligand_pos']) == 2 and len(out['layer_pred_ligand_v']) == 2
+    assert torch.equal(out['layer_pred_ligand_pos'][1], out['pred_ligand_pos'])
+    assert torch.isfinite(out['layer_pred_ligand_v'][0]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_posterior_step_vs_oracle(cuda_lib):
+    from oracle import shapemol_oracle as orc
+    from shapemol_b200.engine import BatchDesc
+    fx = load_golden('forward_k32_train.pt')
+    m = build_model(fx)
+    eng = m._engine()
+    sizes = fx['sizes']
+    bd = BatchDesc(batch_of(sizes))
+    N = sum(sizes)
+    g = torch.Generator().manual_seed(1)
+    tabs = orc.schedule_tables(1000, orc.DEFAULT_CFG['schedule_pos'], orc.DEFAULT_CFG['schedule_v'])
+    for tvals in ([999, 500, 1, 0, 250, 750], [0] * 6, [1] * 6):
+        t = torch.tensor(tvals)
+        x0, logits = torch.randn(N, 3, generator=g), 3 * torch.randn(N, 15, generator=g)
+        xt, vt = torch.randn(N, 3, generator=g), torch.randint(0, 15, (N,), generator=g)
+        eps, u = torch.randn(N, 3, generator=g), torch.rand(N, 15, generator=g)
+        u[0, 0] = 0.0
+        t_atoms = t[batch_of(sizes, 'cpu')]
+        ex, ev, elv0, epost = orc.posterior_step(tabs, x0, logits, xt, vt, t_atoms, eps, u)
+        pos, v = xt.cuda().clone(), vt.int().cuda().clone()
+        lv0, post = torch.empty(N, 15, device='cuda'), torch.empty(N, 15, device='cuda')
+        eng.posterior(bd, x0.cuda(), logits.cuda(), t.int().cuda(), pos, v, eps.cuda(), u.cuda(), lv0, post)
+        torch.cuda.synchronize()
+        assert torch.allclose(pos.cpu(), ex, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(lv0.cpu(), elv0, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(post.cpu(), epost, rtol=1e-5, atol=2e-5)
+        # argmax may only differ where the two best perturbed scores are within round-off
+        gum = -torch.log(-torch.log(u + 1e-30) + 1e-30) + epost
+        top2 = gum.topk(2, dim=-1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 1e-4
+        assert torch.equal(v.cpu().long()[safe], ev[safe])
+
+
+def test_philox_noise_statistics(cuda_lib):
+    from shapemol_b200.engine import BatchDesc
+    fx = load_golden('forward_k32_train.pt')
+    m = build_model(fx)
+    eng = m._engine()
+    n_mol, n_at = 4000, 25
+    bd = BatchDesc(batch_of([n_at] * n_mol))
+    N = n_mol * n_at
+    t = torch.full((n_mol,), 500, dtype=torch.int32, device='cuda')
+    zeros3 = torch.zeros(N, 3, device='cuda')
+    logits = torch.zeros(N, 15, device='cuda')
+    pos, v = zeros3.clone(), torch.zeros(N, dtype=torch.int32, device='cuda')
+    eng.posterior(bd, zeros3, logits, t, pos, v, seed=7)
+    sig = math.exp(0.5 * float(m.posterior_logvar[500]))
+    z = (pos / sig).cpu()
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.1
+    counts = torch.bincount(v.cpu().long(), minlength=15).float() / N
+    # posterior of uniform logits with v_t = 0 is not uniform; compare against the analytic posterior
+    lv0 = torch.full((1, 15), -math.log(15.0))
+    post = m.cpu().q_v_posterior(lv0, torch.log(torch.nn.functional.one_hot(torch.tensor([0]), 15).float().clamp(min=1e-30)),
+                                 torch.tensor([500]), torch.tensor([0])).exp()[0]
+    assert float((counts - post).abs().max()) < 0.01
+    # different seeds / offsets give different streams, same seed is reproducible
+    pos2, v2 = zeros3.clone(), torch.zeros(N, dtype=torch.int32, device='cuda')
+    m.cuda()
+    eng.posterior(bd, zeros3, logits, t, pos2, v2, seed=7)
+    assert torch.equal(pos, pos2) and torch.equal(v, v2)
+    eng.posterior(bd, zeros3, logits, t, pos2.zero_(), v2.zero_(), seed=8)
+    assert not torch.equal(pos, pos2)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_trajectory_teacher_forced_and_free_running(cuda_lib):
+    """12 reverse steps with the reference's injected noise (tests/golden/trajectory.pt)."""
+    fx = load_golden('trajectory.pt')
+    m = build_model(dict(fx, training=True))
+    sizes, steps = fx['sizes'], fx['steps']
+    batch = batch_of(sizes)
+    # --- teacher-forced: every step starts from the reference's state ---
+    pos, v = fx['pos0'], fx['v0']
+    for s in range(steps):
+        t = torch.full((len(sizes),), 999 - s, dtype=torch.long, device='cuda')
+        out = m(pos.cuda(), v.cuda(), batch, fx['shape'].cuda(), time_step=t)
+        assert rel_err(out['pred_ligand_pos'], fx['pos_cond_traj'][s]) < REL_FP32, s
+        assert rel_err(out['pred_ligand_v'], fx['v_cond_traj'][s]) < REL_FP32, s
+        pos, v = fx['pos_traj'][s], fx['v_traj'][s]
+    # --- free-running through the public sample_diffusion API with the same noise ---
+    m2 = build_model(dict(fx, training=True))
+    m2.smb_noise = lambda s: (fx['noise_pos'][s].cuda(), fx['noise_u'][s].cuda())
+    r = m2.sample_diffusion(init_ligand_pos=fx['pos0'].cuda(), init_ligand_v=fx['v0'].cuda(), batch_ligand=batch,
+                            ligand_shape=fx['shape'].view(-1, 3).cuda(), num_steps=steps, center_pos_mode='none')
+    assert len(r['pos_traj']) == steps and r['pos_traj'][0].device.type == 'cpu' and r['v_traj'][0].dtype == torch.long
+    assert r['pos_cond_traj'][0].device.type == 'cuda' and r['pos_uncond_traj'] == [] and r['v_uncond_traj'] == []
+    assert r['v'].dtype == torch.long and r['pos'].device.type == 'cuda'
+    # positions stay close while the discrete types agree; count type flips (round-off level ties)
+    agree = float((torch.stack(r['v_traj']) == fx['v_traj']).float().mean())
+    print('free-running type agreement over %d steps: %.4f' % (steps, agree))
+    assert agree > 0.97
+    assert rel_err(r['pos_traj'][0], fx['pos_traj'][0]) < REL_FP32
+    assert rel_err(r['v0_traj'][0], fx['v0_traj'][0]) < 5e-3
+    assert rel_err(r['vt_traj'][0], fx['vt_traj'][0]) < 5e-3
+
+
+def test_sampler_graph_equals_eager_and_torch_rng_order(cuda_lib):
+    """CUDA-graph replay == eager re-enqueue; noise='torch' consumes the device generator exactly like
+    the reference (randn [N,3] then rand [N,C] per step)."""
+    fx = load_golden('forward_k32_eval.pt')
+    sizes = fx['sizes']
+    batch = batch_of(sizes)
+    N = sum(sizes)
+    g = torch.Generator().manual_seed(5)
+    pos0, v0 = torch.randn(N, 3, generator=g).cuda(), torch.randint(0, 15, (N,), generator=g).cuda()
+    res = []
+    for use_graph in (False, True):
+        m = build_model(fx, training=False)
+        m.smb_use_graph = use_graph
+        m.smb_keep_traj = False
+        torch.manual_seed(123)
+        r = m.sample_diffusion(pos0, v0, batch, fx['shape'].view(-1, 3).cuda(), num_steps=6, center_pos_mode='none')
+        res.append((r['pos'].clone(), r['v'].clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    # explicit noise drawn in the reference's order reproduces noise='torch'
+    torch.manual_seed(123)
+    noise = []
+    for _ in range(6):
+        a = torch.randn_like(pos0)
+        b = torch.rand(N, 15, device='cuda')
+        noise.append((a, b))
+    m = build_model(fx, training=False)
+    m.smb_noise = lambda s: noise[s]
+    m.smb_keep_traj = False
+    r = m.sample_diffusion(pos0, v0, batch, fx['shape'].view(-1, 3).cuda(), num_steps=6, center_pos_mode='none')
+    assert torch.equal(r['pos'], res[0][0]) and torch.equal(r['v'], res[0][1])
+
+
+# ---------------------------------------------------------------------------------------------
+def test_properties_at_scale(cuda_lib):
+    """Size-independent properties on a large ragged batch (eval-mode BN => molecules independent):
+    batch-composition invariance, molecule permutation equivariance, SO(3) equivariance."""
+    fx = load_golden('forward_k32_eval.pt')
+    m = build_model(fx, training=False)
+    g = torch.Generator().manual_seed(11)
+    B = 3000
+    sizes = torch.randint(9, 28, (B,), generator=g).tolist()
+    N = sum(sizes)
+    pos = torch.randn(N, 3, generator=g).cuda() * 2
+    v = torch.randint(0, 15, (N,), generator=g).cuda()
+    shape = (0.07 * torch.randn(B, 32, 3, generator=g)).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    batch = batch_of(sizes)
+    full = m(pos, v, batch, shape, time_step=t)
+    assert all(torch.isfinite(x).all() for x in full.values())
+    # (1) a molecule's result does not depend on the rest of the batch
+    ptr = torch.tensor([0] + sizes).cumsum(0)
+    for b in (0, 1234, B - 1):
+        sl = slice(int(ptr[b]), int(ptr[b + 1]))
+        one = m(pos[sl].contiguous(), v[sl].contiguous(), torch.zeros(sizes[b], dtype=torch.long, device='cuda'),
+                shape[b:b + 1].contiguous(), time_step=t[b:b + 1].contiguous())
+        assert torch.allclose(one['pred_ligand_pos'], full['pred_ligand_pos'][sl], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(one['pred_ligand_v'], full['pred_ligand_v'][sl], rtol=1e-5, atol=1e-5)
+    # (2) rotating coordinates and the shape latent rotates x0 and leaves the logits unchanged
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    q = q.cuda()
+    rot = m(pos @ q, v, batch, shape @ q, time_step=t)
+    assert rel_err(rot['pred_ligand_pos'], full['pred_ligand_pos'] @ q) < 1e-3
+    assert rel_err(rot['pred_ligand_v'], full['pred_ligand_v']) < 1e-3
+
+
+def test_train_mode_bn_couples_batch_like_reference(cuda_lib):
+    """Train-mode BatchNorm uses statistics over all atoms of the batch: oracle with the
+    same batch agrees; results differ from eval mode."""
+    from oracle import shapemol_oracle as orc
+    fx = load_golden('forward_k32_train.pt')
+    sd = golden_weights(fx)
+    g = torch.Generator().manual_seed(4)
+    sizes = torch.randint(9, 28, (40,), generator=g).tolist()
+    N = sum(sizes)
+    pos, v = torch.randn(N, 3, generator=g) * 2, torch.randint(0, 15, (N,), generator=g)
+    shape, t = 0.07 * torch.randn(40, 32, 3, generator=g), torch.randint(0, 1000, (40,), generator=g)
+    with torch.no_grad():
+        ex, eh, el = orc.forward(sd, oracle_cfg(fx), pos, v, orc.mol_ptr_from_sizes(sizes), shape, t, training=True)
+    m = build_model(fx, training=True)
+    out = m(pos.cuda(), v.cuda(), batch_of(sizes), shape.cuda(), time_step=t.cuda())
+    assert rel_err(out['pred_ligand_pos'], ex) < REL_FP32
+    assert rel_err(out['pred_ligand_v'], el) < REL_FP32
+    m.eval()
+    out_eval = m(pos.cuda(), v.cuda(), batch_of(sizes), shape.cuda(), time_step=t.cuda())
+    assert rel_err(out_eval['pred_ligand_pos'], ex) > 1e-3

@@ -1,0 +1,111 @@
+"""CPU-side checks: drop-in parameter tree == reference manifest, schedule tables bit-exact, the C ABI
+library loads and exports every declared symbol (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+import types
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, manifest_shapes
+
+
+def ref_like_config(**over):
+    import yaml  # noqa: F401
+    cfg = dict(denoise_type='diffusion', model_mean_type='C0', topo_emb_type=None, gt_noise_type='origin',
+               schedule_pos=dict(beta_schedule='sigmoid', beta_start=1.e-7, beta_end=0.01, s=6),
+               schedule_v=dict(beta_schedule='cosine', s=0.01), num_diffusion_timesteps=1000, loss_v_weight=100.0,
+               v_mode='uniform', v_net_type='mlp', loss_pos_type='mse', sample_time_method='symmetric',
+               loss_weight_type='noise_level', loss_pos_min_weight=0, loss_pos_max_weight=10, time_emb_dim=8,
+               time_emb_mode='simple', center_pos_mode='none', atom_enc_mode='add_aromatic', node_indicator=True,
+               model_type='uni_o2', num_blocks=1, num_layers=8, hidden_dim=128, n_heads=16, edge_feat_dim=0,
+               edge_feat='covalent_bond', num_r_gaussian=20, knn=8, num_node_types=8, act_fn='relu', norm=True,
+               cutoff_mode='knn', ew_net_type='global', r_feat_mode='sparse', energy_h_mode='basic', num_x2h=1, num_h2x=1,
+               num_topo=1, r_max=10.0, x2h_out_fc=False, sync_twoup=False, shape_dim=32, shape_latent_dim=32,
+               shape_mode='attention_residue', shape_type='pointAE_shape', cond_mask_prob=0.0)
+    cfg.update(over)
+    return types.SimpleNamespace(**cfg)
+
+
+def make_dropin(**over):
+    from shapemol_b200 import dropin
+    dropin.install()
+    import models.molopt_score_model as msm
+    return msm.ScorePosNet3D(ref_like_config(**over), ligand_atom_feature_dim=15), msm
+
+
+def test_dropin_state_dict_matches_reference_manifest():
+    m, _ = make_dropin(knn=32)
+    sd = m.state_dict()
+    ref = manifest_shapes()
+    assert list(sd.keys()) == list(ref.keys())
+    for k, shp in ref.items():
+        assert tuple(sd[k].shape) == shp, k
+
+
+def test_dropin_schedule_tables_bit_exact():
+    m, _ = make_dropin()
+    ref = load_golden('schedules.pt')
+    sd = m.state_dict()
+    for k, v in ref.items():
+        assert torch.equal(sd[k], v), k
+
+
+def test_dropin_strict_load_and_unsupported_configs():
+    import synth
+    m, _ = make_dropin(knn=32)
+    sd = synth.synth_state_dict(manifest_shapes(), 5, skip_non_synth=False)
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        make_dropin(topo_emb_type='topo_layer')
+    with pytest.raises(NotImplementedError):
+        make_dropin(cutoff_mode='cov_radius')
+    with pytest.raises(NotImplementedError):
+        make_dropin(v_mode='tomask')
+
+
+def test_library_exports_every_declared_symbol():
+    from shapemol_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'shapemol_b200.h')).read()
+    declared = set(re.findall(r'SMB_API\s+[\w\s\*]+?\b(smb_\w+)\s*\(', hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.smb_abi_version() == 1
+
+
+def test_param_enumeration_and_packing_host_side():
+    """smb_param_name enumerates reference state_dict keys; packing is pure host code (no GPU)."""
+    from shapemol_b200 import _lib
+    import synth
+    lib = _lib.load()
+    dims = _lib.ModelDims(hidden=128, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=_lib.PREC_BF16X3)
+    n = lib.smb_param_count(C.byref(dims))
+    names = [lib.smb_param_name(C.byref(dims), i).decode() for i in range(n)]
+    ref = manifest_shapes()
+    assert all(k in ref for k in names)
+    sd = synth.synth_state_dict(ref, 7)
+    host = [sd[k].contiguous() for k in names]
+    arr = (C.c_void_p * n)(*[t.data_ptr() for t in host])
+    nbytes = lib.smb_packed_weights_bytes(C.byref(dims))
+    blob = torch.zeros(nbytes, dtype=torch.uint8)
+    assert lib.smb_pack_weights(C.byref(dims), arr, n, blob.data_ptr(), nbytes) == 0
+    assert int(blob.count_nonzero()) > nbytes // 4
+    # the bf16 layout is half the size of the split layout for the fragment part
+    dims2 = _lib.ModelDims(hidden=128, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=_lib.PREC_BF16)
+    assert lib.smb_packed_weights_bytes(C.byref(dims2)) < nbytes
+    # unsupported configuration -> error code + message, no crash
+    bad = _lib.ModelDims(hidden=64, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=0)
+    assert lib.smb_param_count(C.byref(bad)) == -1
+    assert b'hidden' in lib.smb_last_error_string()
+
+
+def test_product_path_has_no_cpu_fallback():
+    m, _ = make_dropin(knn=32)
+    pos = torch.randn(5, 3)
+    with pytest.raises(Exception) as ei:
+        m(pos, torch.zeros(5, dtype=torch.long), torch.zeros(5, dtype=torch.long), torch.zeros(1, 32, 3),
+          time_step=torch.zeros(1, dtype=torch.long))
+    assert 'CUDA' in str(ei.value) or 'cuda' in str(ei.value)
