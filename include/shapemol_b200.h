@@ -129,7 +129,18 @@ typedef struct smb_forward_io {
   float* bn_running_var[SMB_MAX_LAYERS];
   int64_t* bn_num_batches_tracked[SMB_MAX_LAYERS]; /* may be NULL */
   int32_t training;
+  /* Optional per-kernel timing (bench.py's roofline line): when prof_kernel != 0 the library records
+   * the cudaEvent_t pair prof_events[2i], prof_events[2i+1] on `stream` around its i-th launch of that
+   * kernel class inside this call (i < prof_capacity).  Classes: SMB_PROF_*. */
+  int32_t prof_kernel;
+  int32_t prof_capacity;
+  void* const* prof_events;
 } smb_forward_io;
+
+enum {
+  SMB_PROF_NONE = 0, SMB_PROF_EDGE_K = 1, SMB_PROF_EDGE_V = 2, SMB_PROF_EDGE_XV = 3, SMB_PROF_NODE_PRE = 4,
+  SMB_PROF_NODE_OUT = 5, SMB_PROF_GATE = 6, SMB_PROF_KNN = 7, SMB_PROF_HEAD = 8
+};
 
 SMB_API int smb_forward(const smb_model_dims* dims, const void* packed_weights_dev, const smb_batch* batch,
                 const smb_forward_io* io, void* workspace, size_t workspace_bytes, void* stream);

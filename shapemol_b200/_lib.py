@@ -33,7 +33,10 @@ class ForwardIO(C.Structure):
                 ('pred_pos', _fp), ('pred_h', _fp), ('pred_v', _fp), ('h0', _fp), ('nbr', _fp),
                 ('bn_weight', _fp * SMB_MAX_LAYERS), ('bn_bias', _fp * SMB_MAX_LAYERS),
                 ('bn_running_mean', _fp * SMB_MAX_LAYERS), ('bn_running_var', _fp * SMB_MAX_LAYERS),
-                ('bn_num_batches_tracked', _fp * SMB_MAX_LAYERS), ('training', C.c_int32)]
+                ('bn_num_batches_tracked', _fp * SMB_MAX_LAYERS), ('training', C.c_int32),
+                ('prof_kernel', C.c_int32), ('prof_capacity', C.c_int32), ('prof_events', C.POINTER(_fp))]
+
+PROF = {'edge_k': 1, 'edge_v': 2, 'edge_xv': 3, 'node_pre': 4, 'node_out': 5, 'gate': 6, 'knn': 7, 'head': 8}
 
 
 class PosteriorIO(C.Structure):

@@ -71,6 +71,15 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
 
   SMB_CUDA_OK(cudaMemcpyAsync(x, io.pos, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
+  int prof_i = 0;
+  auto prof = [&](int cls, bool begin) -> int {
+    if (io.prof_kernel != cls || !io.prof_events || prof_i >= io.prof_capacity) return 0;
+    cudaError_t e = cudaEventRecord((cudaEvent_t)io.prof_events[2 * prof_i + (begin ? 0 : 1)], st);
+    if (!begin) ++prof_i;
+    return (int)e;
+  };
+#define SMB_TIMED(cls, expr) do { SMB_LAUNCH(prof(cls, true)); SMB_LAUNCH(expr); SMB_LAUNCH(prof(cls, false)); } while (0)
+
   PrepArgs pa;
   pa.n_mols = B; pa.t = io.t; pa.shape = io.shape;
   pa.time_freq = fptr(blob, L.time_freq); pa.time_w1 = fptr(blob, L.time_w1); pa.time_b1 = fptr(blob, L.time_b1);
@@ -85,7 +94,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   ea.emb_wT = fptr(blob, L.emb_wT); ea.emb_b = fptr(blob, L.emb_b); ea.h = hbuf[0]; ea.h0 = io.h0;
   SMB_LAUNCH(launch_embed(ea, st));
 
-  SMB_LAUNCH(launch_knn(x, b.mol_ptr, B, d.k, nbr, deg, st));
+  SMB_TIMED(SMB_PROF_KNN, launch_knn(x, b.mol_ptr, B, d.k, nbr, deg, st));
   if (io.nbr) SMB_CUDA_OK(cudaMemcpyAsync(io.nbr, nbr, (size_t)N * (d.k + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
 
   EdgeArgs eb;
@@ -97,7 +106,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   {  // global edge gate, computed once from the input coordinates (uni_transformer.py:507)
     EdgeArgs e = eb;
     fill_edge_weights(e, blob, L.gate);
-    SMB_LAUNCH(launch_edge(d, ROLE_GATE, e, nullptr, st));
+    SMB_TIMED(SMB_PROF_GATE, launch_edge(d, ROLE_GATE, e, nullptr, st));
   }
 
   int cur = 0;
@@ -115,26 +124,26 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
       fill_node_weights(n, blob, y.x2h_pre);
-      SMB_LAUNCH(launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
     {
       EdgeArgs e = eb;
       e.col_a = 0; e.col_b = H;
       fill_edge_weights(e, blob, y.hk);
-      SMB_LAUNCH(launch_edge(d, ROLE_K, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_K, launch_edge(d, ROLE_K, e, nullptr, st));
     }
     {
       EdgeArgs e = eb;
       e.col_a = 2 * H; e.col_b = 3 * H;
       fill_edge_weights(e, blob, y.hv);
-      SMB_LAUNCH(launch_edge(d, ROLE_V, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_V, launch_edge(d, ROLE_V, e, nullptr, st));
     }
     {
       NodeArgs n = na;
       n.x_mode = XMODE_AGG_H; n.act = ACT_LN_RELU; n.n_pass = 0; n.n2 = H; n.n2_valid = H;
       n.xa = agg; n.xb = h_in; n.residual = h_in; n.out2 = h_out;
       fill_node_weights(n, blob, y.node_out);
-      SMB_LAUNCH(launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_OUT, launch_node_mlp(d, n, st));
     }
     // ---- H2X (uses the updated h) ----
     {
@@ -142,13 +151,13 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
       fill_node_weights(n, blob, y.h2x_pre);
-      SMB_LAUNCH(launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
     {
       EdgeArgs e = eb;
       e.col_a = 0; e.col_b = H;
       fill_edge_weights(e, blob, y.xk);
-      SMB_LAUNCH(launch_edge(d, ROLE_K, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_K, launch_edge(d, ROLE_K, e, nullptr, st));
     }
     int grid = 0;
     {
@@ -156,7 +165,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       e.col_a = 2 * H; e.col_b = 3 * H;
       e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
       fill_edge_weights(e, blob, y.xv);
-      SMB_LAUNCH(launch_edge(d, ROLE_XV, e, &grid, st));
+      SMB_TIMED(SMB_PROF_EDGE_XV, launch_edge(d, ROLE_XV, e, &grid, st));
     }
     {
       BnArgs bn;
@@ -177,7 +186,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
     n.x_mode = XMODE_H; n.act = ACT_SSP; n.n_pass = 0; n.n2 = 16; n.n2_valid = d.classes;
     n.xa = io.pred_h; n.out2 = io.pred_v;
     fill_node_weights(n, blob, L.head);
-    SMB_LAUNCH(launch_node_mlp(d, n, st));
+    SMB_TIMED(SMB_PROF_HEAD, launch_node_mlp(d, n, st));
   }
   return 0;
 }
@@ -240,7 +249,7 @@ int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batch, const
     return SMB_E_BADARG;
   }
   smb::PosteriorArgs a;
-  a.n_atoms = batch->n_atoms; a.classes = dims->classes; a.atom_mol = batch->atom_mol; a.t = io->t;
+  a.n_atoms = batch->n_atoms; a.classes = dims->classes; a.timesteps = dims->timesteps; a.atom_mol = batch->atom_mol; a.t = io->t;
   a.pred_pos = io->pred_pos; a.pred_v = io->pred_v; a.pos = io->pos; a.v = io->v;
   a.noise_pos = io->noise_pos; a.noise_u = io->noise_u; a.log_v0 = io->log_v0; a.log_post = io->log_post;
   a.seed = io->seed; a.atom_offset = io->atom_offset;

@@ -40,7 +40,7 @@ struct BnArgs {
 };
 
 struct PosteriorArgs {
-  int n_atoms, classes;
+  int n_atoms, classes, timesteps;
   const int* atom_mol;
   const int* t;
   const float* pred_pos;

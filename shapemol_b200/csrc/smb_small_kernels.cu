@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(128) posterior_kernel(PosteriorArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_atoms) return;
   const int C = a.classes;
-  const int t = a.t[a.atom_mol[i]];
+  int t = a.t[a.atom_mol[i]];
+  t = t < 0 ? 0 : (t >= a.timesteps ? a.timesteps - 1 : t);   // table bounds
   const int tm1 = t - 1 < 0 ? 0 : t - 1;
   // ---- noise ----
   float eps[3], u[16];

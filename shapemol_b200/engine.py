@@ -98,7 +98,7 @@ class DenoiseEngine:
         return [blk.h2x_layers[0].shape_linear.batchnorm.bn for blk in self.module.refine_net.base_block]
 
     # ---- one network evaluation --------------------------------------------------------------
-    def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None):
+    def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None, prof=None):
         dims = self.dims()
         dev = pos.device
         blob = self.packed_weights(dev)
@@ -115,6 +115,10 @@ class DenoiseEngine:
             io.bn_running_mean[l], io.bn_running_var[l] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             io.bn_num_batches_tracked[l] = bn.num_batches_tracked.data_ptr()
         io.training = int(self.module.training if training is None else training)
+        if prof is not None:      # (kernel class name, [torch.cuda.Event pairs, already created])
+            cls, events = prof
+            handles = (C.c_void_p * len(events))(*[ev.cuda_event for ev in events])
+            io.prof_kernel, io.prof_capacity, io.prof_events = _lib.PROF[cls], len(events) // 2, handles
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.smb_forward(C.byref(dims), blob.data_ptr(), C.byref(bd.c), C.byref(io), ws.data_ptr(), ws.numel(), stream),
                    'smb_forward')
@@ -239,3 +243,40 @@ class Sampler:
         with torch.cuda.graph(g):
             self._step_body(step)
         self.graph = g
+
+
+class HostStepper:
+    """One denoising step with HOST buffers on both sides (the end-to-end call bench.py times):
+    pinned host (x_t, v_t, t, shape) -> H2D -> network + posterior -> D2H (x_{t-1}, v_{t-1})."""
+
+    def __init__(self, engine, batch_ligand_dev, n_mols, noise='philox', seed=0):
+        m = engine.module
+        self.e = engine
+        self.bd = BatchDesc(batch_ligand_dev, n_mols)
+        dev = batch_ligand_dev.device
+        N, B, Cn, H = self.bd.n_atoms, self.bd.n_mols, m.num_classes, m.hidden_dim
+        self.d_pos = torch.empty(N, 3, device=dev)
+        self.d_v = torch.empty(N, dtype=torch.int32, device=dev)
+        self.d_t = torch.empty(B, dtype=torch.int32, device=dev)
+        self.d_shape = torch.empty(B, 32, 3, device=dev)
+        self.pred_pos = torch.empty(N, 3, device=dev)
+        self.pred_h = torch.empty(N, H, device=dev)
+        self.pred_v = torch.empty(N, Cn, device=dev)
+        self.h_pos_out = torch.empty(N, 3).pin_memory()
+        self.h_v_out = torch.empty(N, dtype=torch.int32).pin_memory()
+        self.seed = seed
+        self.h2d_bytes = N * 12 + N * 4 + B * 4 + B * 32 * 3 * 4
+        self.d2h_bytes = N * 12 + N * 4
+
+    def step(self, h_pos, h_v, h_t, h_shape):
+        """h_*: pinned host tensors.  Returns pinned host (pos_next, v_next); asynchronous on the
+        current stream (synchronise before reading)."""
+        self.d_pos.copy_(h_pos, non_blocking=True)
+        self.d_v.copy_(h_v, non_blocking=True)
+        self.d_t.copy_(h_t, non_blocking=True)
+        self.d_shape.copy_(h_shape, non_blocking=True)
+        self.e.forward(self.d_pos, self.d_v, self.bd, self.d_shape, self.d_t, self.pred_pos, self.pred_h, self.pred_v)
+        self.e.posterior(self.bd, self.pred_pos, self.pred_v, self.d_t, self.d_pos, self.d_v, seed=self.seed)
+        self.h_pos_out.copy_(self.d_pos, non_blocking=True)
+        self.h_v_out.copy_(self.d_v, non_blocking=True)
+        return self.h_pos_out, self.h_v_out
