@@ -37,8 +37,8 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 // B (16x8,  col): b0=(k=2t..2t+1, n=g) b1=(k=2t+8..2t+9, n=g)
 // C (16x8):       c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)      g=lane>>2, t=lane&3
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  // not volatile: the scheduler may interleave independent accumulator chains
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -52,6 +52,21 @@ __device__ __forceinline__ void mma_step(float (&c)[4], const uint32_t (&ahi)[4]
     mma_bf16(c, ahi, bw.z, bw.w);
   }
   mma_bf16(c, ahi, bw.x, bw.y);
+}
+
+// One K=16 step for NC independent accumulators sharing the A operand (one B fragment each); the
+// three split terms are issued term-major so that consecutive MMAs never depend on each other.
+template <bool X3, int NC>
+__device__ __forceinline__ void mma_step_n(float (&c)[NC][4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                           const uint4 (&bw)[NC]) {
+  if (X3) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q) mma_bf16(c[q], alo, bw[q].x, bw[q].y);
+#pragma unroll
+    for (int q = 0; q < NC; ++q) mma_bf16(c[q], ahi, bw[q].z, bw[q].w);
+  }
+#pragma unroll
+  for (int q = 0; q < NC; ++q) mma_bf16(c[q], ahi, bw[q].x, bw[q].y);
 }
 
 __device__ __forceinline__ float quad_sum(float v) {

@@ -32,6 +32,11 @@ constexpr int HP = H + 8;       // padded row stride of the A/B tiles (conflict-
 constexpr int LS = 17;          // padded row stride of the per-warp logit / alpha scratch
 constexpr int MAXSLOT = 64;
 constexpr int WARPS = kEdgeWarps;
+constexpr int MT = 1;          // m-tiles (16 rows) per sub-tile: 1 keeps the warp at <=128 registers (16 warps/SM)
+constexpr int R = 16 * MT;     // neighbour slots (rows) per sub-tile
+constexpr int NR = 2 * MT;     // rows per thread
+constexpr int NGK = 4;         // heads (n-tiles) of the second GEMM in flight: independent MMA chains
+constexpr int NGV = 4;
 
 template <bool X3> struct Frag { using type = uint4; };
 template <> struct Frag<false> { using type = uint2; };
@@ -44,8 +49,13 @@ __device__ __forceinline__ uint4 ld_frag(const typename Frag<X3>::type* p) {
 struct SmemPlan {
   size_t w1r, w2, vecs, tiles, xs, warp, vnw, shape, total;
   size_t warp_stride;
+  int rows;       // atom rows of the staged group tile
+  int mols;       // molecules staged together (a "group")
+  int slot_cap;   // neighbour slots held in the per-warp scratch
 };
-__host__ __device__ inline SmemPlan plan_smem(int role, bool x3, int n_max) {
+constexpr int GROUP_ROWS = 64;
+constexpr int MAX_GROUP_MOLS = 8;
+__host__ __device__ inline SmemPlan plan_smem(int role, bool x3, int n_max, int k) {
   const size_t fb = x3 ? 16 : 8;
   SmemPlan p;
   size_t o = 0;
@@ -55,17 +65,25 @@ __host__ __device__ inline SmemPlan plan_smem(int role, bool x3, int n_max) {
   else if (role == ROLE_XV) o += (size_t)2 * KS2 * 32 * fb;
   else o += H * 4;
   p.vecs = o; o += 3 * H * 4;                        // ln_g | ln_b | b2 (gate: b1)
-  p.tiles = o; if (role != ROLE_GATE) o += (size_t)2 * n_max * HP * 4;
-  p.xs = o; o += (size_t)n_max * 4 * 4;
+  if (n_max < 1) n_max = 1;
+  p.mols = GROUP_ROWS / n_max;
+  if (p.mols < 1) p.mols = 1;
+  if (p.mols > MAX_GROUP_MOLS) p.mols = MAX_GROUP_MOLS;
+  p.rows = p.mols * n_max;
+  int deg_max = k + 1 < n_max ? k + 1 : n_max;       // deg <= min(k+1, n-1) (k+1 only for coincident duplicates)
+  p.slot_cap = (deg_max + 31) / 32 * 32;
+  if (p.slot_cap > MAXSLOT) p.slot_cap = MAXSLOT;
+  p.tiles = o; if (role != ROLE_GATE) o += (size_t)2 * p.rows * HP * 4;
+  p.xs = o; o += (size_t)p.rows * 4 * 4;
   p.vnw = o; if (role == ROLE_XV) o += (size_t)2 * kHeads * kVnStride * 4;
   o = (o + 15) / 16 * 16;
-  p.shape = o; if (role == ROLE_XV) o += kShape * 3 * 4;
+  p.shape = o; if (role == ROLE_XV) o += (size_t)p.mols * kShape * 3 * 4;
   o = (o + 15) / 16 * 16;
   p.warp = o;
   size_t ws = 0;
-  if (role == ROLE_K) ws = H * 4 + (size_t)MAXSLOT * LS * 4;
-  else if (role == ROLE_V) ws = (size_t)MAXSLOT * LS * 4;
-  else if (role == ROLE_XV) ws = (size_t)MAXSLOT * LS * 4 + kHeads * 4 * 4;
+  if (role == ROLE_K) ws = H * 4 + (size_t)p.slot_cap * LS * 4;
+  else if (role == ROLE_V) ws = (size_t)p.slot_cap * LS * 4 + H * 4;
+  else if (role == ROLE_XV) ws = (size_t)p.slot_cap * LS * 4 + kHeads * 4 * 4;
   ws = (ws + 15) / 16 * 16;
   p.warp_stride = ws;
   o += ws * WARPS;
@@ -75,9 +93,10 @@ __host__ __device__ inline SmemPlan plan_smem(int role, bool x3, int n_max) {
 
 template <int ROLE, bool X3>
 __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
+  static_assert(WARPS * 32 * 128 <= 65536, "register budget");
   using F = typename Frag<X3>::type;
   extern __shared__ __align__(16) unsigned char smem[];
-  const SmemPlan P = plan_smem(ROLE, X3, a.n_max);
+  const SmemPlan P = plan_smem(ROLE, X3, a.n_max, a.k);
   F* s_w1r = reinterpret_cast<F*>(smem + P.w1r);
   F* s_w2 = reinterpret_cast<F*>(smem + P.w2);
   float* s_w2vec = reinterpret_cast<float*>(smem + P.w2);     // gate only
@@ -85,7 +104,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
   float* s_be = s_g + H;
   float* s_b2 = s_be + H;
   float* s_A = reinterpret_cast<float*>(smem + P.tiles);
-  float* s_B = s_A + (size_t)a.n_max * HP;
+  float* s_B = s_A + (size_t)P.rows * HP;
   float* s_x = reinterpret_cast<float*>(smem + P.xs);
   float* s_vnw = reinterpret_cast<float*>(smem + P.vnw);
   float* s_shape = reinterpret_cast<float*>(smem + P.shape);
@@ -94,7 +113,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
   float* s_warp = reinterpret_cast<float*>(smem + P.warp + (size_t)warp * P.warp_stride);
   float* s_q = s_warp;                                        // ROLE_K
   float* s_l = ROLE == ROLE_K ? s_warp + H : s_warp;          // logits (K) / alpha (V, XV)
-  float* s_o = s_warp + MAXSLOT * LS;                         // ROLE_XV: o[16][4]
+  float* s_o = s_warp + P.slot_cap * LS;                      // ROLE_XV: o[16][4]
+  float* s_out = s_warp + P.slot_cap * LS;                    // ROLE_V: per-destination accumulator [H]
   const int KSTR = a.k + 1;
 
   // ---- stage the weights once per CTA ----
@@ -129,11 +149,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
   const float gate_b2 = ROLE == ROLE_GATE ? a.b2[0] : 0.f;
   float bn_s = 0.f, bn_q = 0.f;   // ROLE_XV: per-warp partial sums (lane = channel)
 
+  const int n_groups = (a.n_mols + P.mols - 1) / P.mols;
 #pragma unroll 1
-  for (int m = blockIdx.x; m < a.n_mols; m += gridDim.x) {
-    const int a0 = a.mol_ptr[m];
-    const int n = a.mol_ptr[m + 1] - a0;
-    __syncthreads();   // previous molecule's tiles are free (also orders the weight staging)
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int m0 = grp * P.mols;
+    const int m1 = min(m0 + P.mols, a.n_mols);
+    const int a0 = a.mol_ptr[m0];
+    const int n = a.mol_ptr[m1] - a0;            // atoms of the group (<= P.rows)
+    __syncthreads();   // previous group's tiles are free (also orders the weight staging)
     for (int p = tid; p < n * 3; p += blockDim.x) s_x[(p / 3) * 4 + (p % 3)] = a.x[(size_t)a0 * 3 + p];
     if (ROLE != ROLE_GATE) {
       const int n4 = n * (H / 4);
@@ -145,14 +168,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
       }
     }
     if (ROLE == ROLE_XV)
-      for (int p = tid; p < kShape * 3; p += blockDim.x) s_shape[p] = a.shape[(size_t)m * kShape * 3 + p];
+      for (int p = tid; p < (m1 - m0) * kShape * 3; p += blockDim.x) s_shape[p] = a.shape[(size_t)m0 * kShape * 3 + p];
     __syncthreads();
 
 #pragma unroll 1
-    for (int i = warp; i < n; i += WARPS) {
+    for (int i = warp; i < n; i += WARPS) {        // i: group-local atom index
       const int gi = a0 + i;
-      const int dg = min(a.deg[gi], MAXSLOT);
-      const int nsub = (dg + 31) >> 5;
+      int mloc = 0;                                 // molecule of atom i within the group
+      while (m0 + mloc + 1 < m1 && a.mol_ptr[m0 + mloc + 1] <= gi) ++mloc;
+      const int moff = a.mol_ptr[m0 + mloc] - a0;   // group-local index of the molecule's first atom
+      const int dg = min(a.deg[gi], P.slot_cap);
+      const int nsub = (dg + R - 1) / R;
       const int* nb = a.nbr + (size_t)gi * KSTR;
       const float xi = s_x[i * 4], yi = s_x[i * 4 + 1], zi = s_x[i * 4 + 2];
 
@@ -161,19 +187,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
       }
       if (ROLE == ROLE_V || ROLE == ROLE_XV) {
         const float* al = a.alpha + (size_t)gi * KSTR * kHeads;
-        for (int p = lane; p < nsub * 32 * kHeads; p += 32) {
+        for (int p = lane; p < nsub * R * kHeads; p += 32) {
           const int slot = p >> 4, hd = p & 15;
           s_l[slot * LS + hd] = slot < dg ? al[p] : 0.f;
         }
       }
+      if (ROLE == ROLE_V) *reinterpret_cast<float4*>(s_out + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
 
-      float outacc[ROLE == ROLE_V ? NT : 1][2];
       float oacc[ROLE == ROLE_XV ? 4 : 1][3];
-      if (ROLE == ROLE_V) {
-#pragma unroll
-        for (int q = 0; q < NT; ++q) { outacc[q][0] = 0.f; outacc[q][1] = 0.f; }
-      }
       if (ROLE == ROLE_XV) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { oacc[q][0] = 0.f; oacc[q][1] = 0.f; oacc[q][2] = 0.f; }
@@ -181,22 +203,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
 
 #pragma unroll 1
       for (int s = 0; s < nsub; ++s) {
-        // ---- rows of this thread: slot = 32 s + g + 8 r2 ----
-        int jr[4];
-        float rel[4][3], dist[4];
+        // ---- rows of this thread: slot = R s + g + 8 r2 ----
+        int jr[NR];
+        float rel[NR][3], dist[NR];
 #pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) {
-          const int slot = s * 32 + g + 8 * r2;
-          const int j = slot < dg ? nb[slot] : -1;
+        for (int r2 = 0; r2 < NR; ++r2) {
+          const int slot = s * R + g + 8 * r2;
+          const int j = slot < dg ? nb[slot] + moff : -1;
           jr[r2] = j;
           const int jj = j < 0 ? 0 : j;
           rel[r2][0] = xi - s_x[jj * 4]; rel[r2][1] = yi - s_x[jj * 4 + 1]; rel[r2][2] = zi - s_x[jj * 4 + 2];
           dist[r2] = sqrtf(rel[r2][0] * rel[r2][0] + rel[r2][1] * rel[r2][1] + rel[r2][2] * rel[r2][2]);
         }
         // ---- A fragments of GEMM1: rbf(dist), K = 20 padded to 32 ----
-        uint32_t a1hi[2][2][4], a1lo[2][2][4];
+        uint32_t a1hi[MT][2][4], a1lo[MT][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -205,39 +227,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
               const int k0 = ks * 16 + 2 * t + ((e >> 1) ? 8 : 0);
               float v0 = 0.f, v1 = 0.f;
               if (k0 < kRbf && jr[r2] >= 0) {
+                // exp(-0.5 d^2) = 2^(-0.5 log2(e) d^2)
                 const float d0 = dist[r2] - rbf_centre(k0), d1 = dist[r2] - rbf_centre(k0 + 1);
-                v0 = expf(-0.5f * d0 * d0);
-                v1 = expf(-0.5f * d1 * d1);
+                v0 = exp2f(-0.72134752044448170f * d0 * d0);
+                v1 = exp2f(-0.72134752044448170f * d1 * d1);
               }
               split_bf16x2(v0, v1, a1hi[mt][ks][e], a1lo[mt][ks][e]);
             }
-        // ---- GEMM1 ----
-        float acc[2][NT][4];
+        // ---- GEMM1 (4 n-tiles = 4*MT independent accumulator chains in flight) ----
+        float acc[MT][NT][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { acc[0][nt][e] = 0.f; acc[1][nt][e] = 0.f; }
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+        for (int nb4 = 0; nb4 < NT; nb4 += 4) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint4 bw = ld_frag<X3>(s_w1r + (nt * 2 + ks) * 32 + lane);
-            mma_step<X3>(acc[0][nt], a1hi[0][ks], a1lo[0][ks], bw);
-            mma_step<X3>(acc[1][nt], a1hi[1][ks], a1lo[1][ks], bw);
+            uint4 bw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bw[q] = ld_frag<X3>(s_w1r + ((nb4 + q) * 2 + ks) * 32 + lane);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              mma_step_n<X3, 4>(*reinterpret_cast<float(*)[4][4]>(&acc[mt][nb4]), a1hi[mt][ks], a1lo[mt][ks], bw);
           }
         }
         // ---- + A_i + B_j (gate: + b1), LayerNorm statistics ----
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        float sum[NR];
+#pragma unroll
+        for (int r2 = 0; r2 < NR; ++r2) sum[r2] = 0.f;
         {
           const float* Ai = s_A + i * HP + 2 * t;
-          const float* Bj[4];
+          const float* Bj[NR];
 #pragma unroll
-          for (int r2 = 0; r2 < 4; ++r2) Bj[r2] = s_B + (jr[r2] < 0 ? 0 : jr[r2]) * HP + 2 * t;
+          for (int r2 = 0; r2 < NR; ++r2) Bj[r2] = s_B + (jr[r2] < 0 ? 0 : jr[r2]) * HP + 2 * t;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             float2 av;
             if (ROLE == ROLE_GATE) av = *reinterpret_cast<const float2*>(s_b2 + nt * 8 + 2 * t);
             else av = *reinterpret_cast<const float2*>(Ai + nt * 8);
 #pragma unroll
-            for (int r2 = 0; r2 < 4; ++r2) {
+            for (int r2 = 0; r2 < NR; ++r2) {
               float2 bv = make_float2(0.f, 0.f);
               if (ROLE != ROLE_GATE) bv = *reinterpret_cast<const float2*>(Bj[r2] + nt * 8);
               float& c0 = acc[r2 >> 1][nt][(r2 & 1) * 2];
@@ -247,21 +279,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
             }
           }
         }
-        float mean[4], rstd[4];
+        float mean[NR], rstd[NR];
 #pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) mean[r2] = quad_sum(sum[r2]) * (1.f / H);
+        for (int r2 = 0; r2 < NR; ++r2) mean[r2] = quad_sum(sum[r2]) * (1.f / H);
         {
-          float var[4] = {0.f, 0.f, 0.f, 0.f};
+          float var[NR];
+#pragma unroll
+          for (int r2 = 0; r2 < NR; ++r2) var[r2] = 0.f;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int r2 = 0; r2 < 4; ++r2) {
+            for (int r2 = 0; r2 < NR; ++r2) {
               const float d0 = acc[r2 >> 1][nt][(r2 & 1) * 2] - mean[r2];
               const float d1 = acc[r2 >> 1][nt][(r2 & 1) * 2 + 1] - mean[r2];
               var[r2] = fmaf(d0, d0, var[r2]); var[r2] = fmaf(d1, d1, var[r2]);
             }
 #pragma unroll
-          for (int r2 = 0; r2 < 4; ++r2) rstd[r2] = 1.f / sqrtf(quad_sum(var[r2]) * (1.f / H) + 1e-5f);
+          for (int r2 = 0; r2 < NR; ++r2) rstd[r2] = 1.f / sqrtf(quad_sum(var[r2]) * (1.f / H) + 1e-5f);
         }
         // ---- normalise + affine + ReLU (in place) ----
 #pragma unroll
@@ -269,7 +303,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
           const float2 gg = *reinterpret_cast<const float2*>(s_g + nt * 8 + 2 * t);
           const float2 be = *reinterpret_cast<const float2*>(s_be + nt * 8 + 2 * t);
 #pragma unroll
-          for (int r2 = 0; r2 < 4; ++r2) {
+          for (int r2 = 0; r2 < NR; ++r2) {
             float& c0 = acc[r2 >> 1][nt][(r2 & 1) * 2];
             float& c1 = acc[r2 >> 1][nt][(r2 & 1) * 2 + 1];
             c0 = fmaxf(fmaf((c0 - mean[r2]) * rstd[r2], gg.x, be.x), 0.f);
@@ -279,24 +313,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
 
         if (ROLE == ROLE_GATE) {
           // ---- e_w = sigmoid(w2 . z + b2) ----
-          float dot[4] = {0.f, 0.f, 0.f, 0.f};
+          float dot[NR];
+#pragma unroll
+          for (int r2 = 0; r2 < NR; ++r2) dot[r2] = 0.f;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             const float2 w = *reinterpret_cast<const float2*>(s_w2vec + nt * 8 + 2 * t);
 #pragma unroll
-            for (int r2 = 0; r2 < 4; ++r2)
+            for (int r2 = 0; r2 < NR; ++r2)
               dot[r2] = fmaf(acc[r2 >> 1][nt][(r2 & 1) * 2], w.x, fmaf(acc[r2 >> 1][nt][(r2 & 1) * 2 + 1], w.y, dot[r2]));
           }
 #pragma unroll
-          for (int r2 = 0; r2 < 4; ++r2) dot[r2] = quad_sum(dot[r2]);
-          const float mine = t == 0 ? dot[0] : (t == 1 ? dot[1] : (t == 2 ? dot[2] : dot[3]));
-          const int slot = s * 32 + g + 8 * t;
-          if (slot < dg) a.ew_out[(size_t)gi * KSTR + slot] = 1.f / (1.f + expf(-(mine + gate_b2)));
+          for (int r2 = 0; r2 < NR; ++r2) {
+            dot[r2] = quad_sum(dot[r2]);
+            const int slot = s * R + g + 8 * r2;
+            if (t == (r2 & 3) && slot < dg) a.ew_out[(size_t)gi * KSTR + slot] = 1.f / (1.f + expf(-(dot[r2] + gate_b2)));
+          }
         } else {
           // ---- re-pack z as A fragments of GEMM2 (accumulator layout == A layout, in registers) ----
-          uint32_t zhi[2][KS2][4], zlo[2][KS2][4];
+          uint32_t zhi[MT][KS2][4], zlo[MT][KS2][4];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int ks = 0; ks < KS2; ++ks) {
               split_bf16x2(acc[mt][2 * ks][0], acc[mt][2 * ks][1], zhi[mt][ks][0], zlo[mt][ks][0]);
@@ -305,59 +342,82 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
               split_bf16x2(acc[mt][2 * ks + 1][2], acc[mt][2 * ks + 1][3], zhi[mt][ks][3], zlo[mt][ks][3]);
             }
 
-          if (ROLE == ROLE_K) {
-#pragma unroll 2
-            for (int nt2 = 0; nt2 < NT; ++nt2) {   // one n-tile == one head (dh = 8)
-              float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          if (ROLE == ROLE_K || ROLE == ROLE_V) {
+            constexpr int NG = ROLE == ROLE_K ? NGK : NGV;
+#pragma unroll 1
+            for (int nb2 = 0; nb2 < NT; nb2 += NG) {   // one n-tile == one head (dh = 8); NG heads in flight
+              float c[MT][NG][4];
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int q = 0; q < NG; ++q)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) c[mt][q][e] = 0.f;
 #pragma unroll
               for (int ks = 0; ks < KS2; ++ks) {
-                const uint4 bw = ld_frag<X3>(s_w2 + (nt2 * KS2 + ks) * 32 + lane);
-                mma_step<X3>(c[0], zhi[0][ks], zlo[0][ks], bw);
-                mma_step<X3>(c[1], zhi[1][ks], zlo[1][ks], bw);
+                uint4 bw[NG];
+#pragma unroll
+                for (int q = 0; q < NG; ++q) bw[q] = ld_frag<X3>(s_w2 + ((nb2 + q) * KS2 + ks) * 32 + lane);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_step_n<X3, NG>(c[mt], zhi[mt][ks], zlo[mt][ks], bw);
               }
-              const float2 qv = *reinterpret_cast<const float2*>(s_q + nt2 * 8 + 2 * t);
-              // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
-              float l0 = quad_sum(fmaf(c[0][0], qv.x, c[0][1] * qv.y));
-              float l1 = quad_sum(fmaf(c[0][2], qv.x, c[0][3] * qv.y));
-              float l2 = quad_sum(fmaf(c[1][0], qv.x, c[1][1] * qv.y));
-              float l3 = quad_sum(fmaf(c[1][2], qv.x, c[1][3] * qv.y));
-              const float mine = t == 0 ? l0 : (t == 1 ? l1 : (t == 2 ? l2 : l3));
-              s_l[(s * 32 + g + 8 * t) * LS + nt2] = mine;
-            }
-          } else if (ROLE == ROLE_V) {
+              if (ROLE == ROLE_K) {
 #pragma unroll
-            for (int nt2 = 0; nt2 < NT; ++nt2) {
-              float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                for (int q = 0; q < NG; ++q) {
+                  const float2 qv = *reinterpret_cast<const float2*>(s_q + (nb2 + q) * 8 + 2 * t);
+                  // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
 #pragma unroll
-              for (int ks = 0; ks < KS2; ++ks) {
-                const uint4 bw = ld_frag<X3>(s_w2 + (nt2 * KS2 + ks) * 32 + lane);
-                mma_step<X3>(c[0], zhi[0][ks], zlo[0][ks], bw);
-                mma_step<X3>(c[1], zhi[1][ks], zlo[1][ks], bw);
-              }
-              const float2 bb = *reinterpret_cast<const float2*>(s_b2 + nt2 * 8 + 2 * t);
+                  for (int r2 = 0; r2 < NR; ++r2) {
+                    const float l = quad_sum(fmaf(c[r2 >> 1][q][(r2 & 1) * 2], qv.x, c[r2 >> 1][q][(r2 & 1) * 2 + 1] * qv.y));
+                    if (t == (r2 & 3)) s_l[(s * R + g + 8 * r2) * LS + nb2 + q] = l;
+                  }
+                }
+              } else {
 #pragma unroll
-              for (int r2 = 0; r2 < 4; ++r2) {
-                const float al = s_l[(s * 32 + g + 8 * r2) * LS + nt2];
-                outacc[nt2][0] = fmaf(al, c[r2 >> 1][(r2 & 1) * 2] + bb.x, outacc[nt2][0]);
-                outacc[nt2][1] = fmaf(al, c[r2 >> 1][(r2 & 1) * 2 + 1] + bb.y, outacc[nt2][1]);
+                for (int q = 0; q < NG; ++q) {
+                  const int nt2 = nb2 + q;
+                  const float2 bb = *reinterpret_cast<const float2*>(s_b2 + nt2 * 8 + 2 * t);
+                  float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                  for (int r2 = 0; r2 < NR; ++r2) {
+                    const float al = s_l[(s * R + g + 8 * r2) * LS + nt2];
+                    v0 = fmaf(al, c[r2 >> 1][q][(r2 & 1) * 2] + bb.x, v0);
+                    v1 = fmaf(al, c[r2 >> 1][q][(r2 & 1) * 2 + 1] + bb.y, v1);
+                  }
+                  v0 = group_sum(v0); v1 = group_sum(v1);
+                  if (g == 0) {
+                    float2* o = reinterpret_cast<float2*>(s_out + nt2 * 8 + 2 * t);
+                    float2 cur = *o;
+                    cur.x += v0; cur.y += v1;
+                    *o = cur;
+                  }
+                }
               }
             }
           } else {   // ROLE_XV: N2 = 16 heads = 2 n-tiles
+            float c[MT][2][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[mt][q][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS2; ++ks) {
+              uint4 bw[2];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) bw[q] = ld_frag<X3>(s_w2 + (q * KS2 + ks) * 32 + lane);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) mma_step_n<X3, 2>(c[mt], zhi[mt][ks], zlo[mt][ks], bw);
+            }
 #pragma unroll
             for (int nt2 = 0; nt2 < 2; ++nt2) {
-              float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-              for (int ks = 0; ks < KS2; ++ks) {
-                const uint4 bw = ld_frag<X3>(s_w2 + (nt2 * KS2 + ks) * 32 + lane);
-                mma_step<X3>(c[0], zhi[0][ks], zlo[0][ks], bw);
-                mma_step<X3>(c[1], zhi[1][ks], zlo[1][ks], bw);
-              }
               const float2 bb = *reinterpret_cast<const float2*>(s_b2 + nt2 * 8 + 2 * t);
 #pragma unroll
-              for (int r2 = 0; r2 < 4; ++r2) {
-                const float* al = s_l + (s * 32 + g + 8 * r2) * LS + nt2 * 8 + 2 * t;
-                const float w0 = al[0] * (c[r2 >> 1][(r2 & 1) * 2] + bb.x);
-                const float w1 = al[1] * (c[r2 >> 1][(r2 & 1) * 2 + 1] + bb.y);
+              for (int r2 = 0; r2 < NR; ++r2) {
+                const float* al = s_l + (s * R + g + 8 * r2) * LS + nt2 * 8 + 2 * t;
+                const float w0 = al[0] * (c[r2 >> 1][nt2][(r2 & 1) * 2] + bb.x);
+                const float w1 = al[1] * (c[r2 >> 1][nt2][(r2 & 1) * 2 + 1] + bb.y);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                   oacc[nt2 * 2][d] = fmaf(w0, rel[r2][d], oacc[nt2 * 2][d]);
@@ -390,11 +450,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
         for (int slot = part; slot < dg; slot += 2) al[slot * kHeads + hd] = s_l[slot * LS + hd] * inv * ew[slot];
         __syncwarp();
       } else if (ROLE == ROLE_V) {
-#pragma unroll
-        for (int nt2 = 0; nt2 < NT; ++nt2) {
-          const float v0 = group_sum(outacc[nt2][0]), v1 = group_sum(outacc[nt2][1]);
-          if (g == 0) *reinterpret_cast<float2*>(a.agg + (size_t)gi * H + nt2 * 8 + 2 * t) = make_float2(v0, v1);
-        }
+        __syncwarp();
+        *reinterpret_cast<float4*>(a.agg + (size_t)gi * H + lane * 4) = *reinterpret_cast<const float4*>(s_out + lane * 4);
         __syncwarp();
       } else if (ROLE == ROLE_XV) {
 #pragma unroll
@@ -409,6 +466,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
         // VN linear maps: lanes 0..15 -> map_to_feat channel, lanes 16..31 -> map_to_dir channel
         const int ch = lane & 15, which = lane >> 4;
         const float* w = s_vnw + (which * kHeads + ch) * kVnStride;
+        const float* shp = s_shape + mloc * kShape * 3;
         float vx = w[0] * xi, vy = w[0] * yi, vz = w[0] * zi;
 #pragma unroll
         for (int c = 0; c < kHeads; ++c) {
@@ -418,7 +476,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
 #pragma unroll 8
         for (int c = 0; c < kShape; ++c) {
           const float wc = w[1 + kHeads + c];
-          vx = fmaf(wc, s_shape[c * 3], vx); vy = fmaf(wc, s_shape[c * 3 + 1], vy); vz = fmaf(wc, s_shape[c * 3 + 2], vz);
+          vx = fmaf(wc, shp[c * 3], vx); vy = fmaf(wc, shp[c * 3 + 1], vy); vz = fmaf(wc, shp[c * 3 + 2], vz);
         }
         float* row = a.vn + (size_t)gi * kVnRow;
         row[3 + which * 48 + ch * 3] = vx; row[4 + which * 48 + ch * 3] = vy; row[5 + which * 48 + ch * 3] = vz;
@@ -435,7 +493,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
         __syncwarp();
       }
     }   // destinations
-  }     // molecules
+  }     // groups
 
   if (ROLE == ROLE_XV && lane < 16) {
     float* part = a.bn_partial + (size_t)(blockIdx.x * WARPS + warp) * 32;
@@ -458,7 +516,7 @@ int num_sms() {
 
 template <int ROLE, bool X3>
 int launch_role(const EdgeArgs& a, int* grid_out, cudaStream_t st) {
-  const SmemPlan P = plan_smem(ROLE, X3, a.n_max);
+  const SmemPlan P = plan_smem(ROLE, X3, a.n_max, a.k);
   if (P.total > 227 * 1024) { set_error_msg("edge kernel: shared memory plan exceeds 227 KB"); return SMB_E_TOOBIG; }
   static size_t configured = 0;
   if (configured < P.total) {
@@ -468,7 +526,8 @@ int launch_role(const EdgeArgs& a, int* grid_out, cudaStream_t st) {
   }
   int grid = num_sms();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
-  if (grid > a.n_mols) grid = a.n_mols;
+  const int n_groups = (a.n_mols + P.mols - 1) / P.mols;
+  if (grid > n_groups) grid = n_groups;
   if (grid_out) *grid_out = grid;
   edge_kernel<ROLE, X3><<<grid, WARPS * 32, P.total, st>>>(a);
   return (int)cudaGetLastError();

@@ -88,7 +88,7 @@ struct Workspace {
 };
 constexpr int kVnRow = 100;
 constexpr int kEdgeMaxCtas = 148 * 2;
-constexpr int kEdgeWarps = 8;
+constexpr int kEdgeWarps = 16;
 Workspace build_workspace(const smb_model_dims& d, int n_atoms, int n_mols);
 
 }  // namespace smb

@@ -49,12 +49,11 @@ template <bool X3, int KSN, int NTN>
 __device__ __forceinline__ void gemm_tile(float (&c)[NTN][4], const uint32_t (&ahi)[KSN][4], const uint32_t (&alo)[KSN][4],
                                           const typename Frag<X3>::type* bt, int lane) {
 #pragma unroll
-  for (int nt = 0; nt < NTN; ++nt) {
+  for (int ks = 0; ks < KSN; ++ks) {
+    uint4 bw[NTN];
 #pragma unroll
-    for (int ks = 0; ks < KSN; ++ks) {
-      const uint4 bw = ld_frag<X3>(bt + (nt * KSN + ks) * 32 + lane);
-      mma_step<X3>(c[nt], ahi[ks], alo[ks], bw);
-    }
+    for (int nt = 0; nt < NTN; ++nt) bw[nt] = ld_frag<X3>(bt + (nt * KSN + ks) * 32 + lane);
+    mma_step_n<X3, NTN>(c, ahi[ks], alo[ks], bw);
   }
 }
 
