@@ -109,3 +109,25 @@ def test_product_path_has_no_cpu_fallback():
         m(pos, torch.zeros(5, dtype=torch.long), torch.zeros(5, dtype=torch.long), torch.zeros(1, 32, 3),
           time_step=torch.zeros(1, dtype=torch.long))
     assert 'CUDA' in str(ei.value) or 'cuda' in str(ei.value)
+
+
+def test_dropin_shape_autoencoder_state_dict_matches_reference():
+    """PointCloud_AE drop-in: same state_dict keys / shapes as the shipped se_model.pt (probed from the
+    reference checkpoint; SURVEY 0.5: the DGCNN blocks are unregistered) and strict loading works."""
+    import synth
+    from shapemol_b200 import dropin
+    dropin.install()
+    import models.shape_pointcloud_modelAE as spm
+    cfg = types.SimpleNamespace(model_type='PointCloud_AE', encoder='VN_DGCNN', loss_type='signed_distance', latent_dim=32,
+                                hidden_dim=128, point_dim=3, layer_num=4, num_k=20)
+    ae = spm.PointCloud_AE(cfg)
+    fx = load_golden('encoder.pt')
+    expect = {'encoder.' + k: tuple(v.shape) for k, v in fx['trained'].items()}
+    expect.update({'generator.z_in.map_to_feat.weight': (32, 32), 'generator.fc_in.weight': (128, 65),
+                   'generator.fc_in.bias': (128,), 'generator.fc_out.weight': (1, 128), 'generator.fc_out.bias': (1,)})
+    sd = ae.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == expect
+    ae.load_state_dict(synth.synth_state_dict(expect, 11, skip_non_synth=False), strict=True)
+    assert len(ae.encoder.blocks) == 4 and not any(k.startswith('encoder.blocks') for k in sd)
+    with pytest.raises(Exception):
+        ae.encoder(torch.zeros(1, 1, 64, 3))     # CPU tensor: the encoder has no CPU path
