@@ -24,6 +24,7 @@ static inline T* wptr(void* base, size_t off) { return reinterpret_cast<T*>(rein
 static void fill_edge_weights(EdgeArgs& e, const void* blob, const EdgeMlpOff& o) {
   e.w1r = vptr(blob, o.w1r); e.b1 = fptr(blob, o.b1); e.ln_g = fptr(blob, o.ln_g); e.ln_b = fptr(blob, o.ln_b);
   e.w2 = vptr(blob, o.w2); e.b2 = fptr(blob, o.b2);
+  e.w1r_u = vptr(blob, o.w1r_u); e.w2_u = vptr(blob, o.w2_u);
 }
 static void fill_node_weights(NodeArgs& n, const void* blob, const NodeMlpOff& o) {
   n.w1 = vptr(blob, o.w1); n.b1 = fptr(blob, o.b1); n.ln_g = fptr(blob, o.ln_g); n.ln_b = fptr(blob, o.ln_b);
@@ -159,17 +160,17 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       fill_edge_weights(e, blob, y.xk);
       SMB_TIMED(SMB_PROF_EDGE_K, launch_edge(d, ROLE_K, e, nullptr, st));
     }
-    int grid = 0;
+    int bn_rows = 0;
     {
       EdgeArgs e = eb;
       e.col_a = 2 * H; e.col_b = 3 * H;
       e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
       fill_edge_weights(e, blob, y.xv);
-      SMB_TIMED(SMB_PROF_EDGE_XV, launch_edge(d, ROLE_XV, e, &grid, st));
+      SMB_TIMED(SMB_PROF_EDGE_XV, launch_edge(d, ROLE_XV, e, &bn_rows, st));
     }
     {
       BnArgs bn;
-      bn.training = io.training; bn.n_atoms = N; bn.rows = grid * kEdgeWarps; bn.partial = bn_part;
+      bn.training = io.training; bn.n_atoms = N; bn.rows = bn_rows; bn.partial = bn_part;
       bn.weight = io.bn_weight[l]; bn.bias = io.bn_bias[l];
       bn.running_mean = io.bn_running_mean[l]; bn.running_var = io.bn_running_var[l];
       bn.num_batches_tracked = io.bn_num_batches_tracked[l];

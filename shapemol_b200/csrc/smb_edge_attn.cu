@@ -515,7 +515,7 @@ int num_sms() {
 }
 
 template <int ROLE, bool X3>
-int launch_role(const EdgeArgs& a, int* grid_out, cudaStream_t st) {
+int launch_role(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
   const SmemPlan P = plan_smem(ROLE, X3, a.n_max, a.k);
   if (P.total > 227 * 1024) { set_error_msg("edge kernel: shared memory plan exceeds 227 KB"); return SMB_E_TOOBIG; }
   static size_t configured = 0;
@@ -528,7 +528,7 @@ int launch_role(const EdgeArgs& a, int* grid_out, cudaStream_t st) {
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
   const int n_groups = (a.n_mols + P.mols - 1) / P.mols;
   if (grid > n_groups) grid = n_groups;
-  if (grid_out) *grid_out = grid;
+  if (bn_rows_out) *bn_rows_out = grid * WARPS;
   edge_kernel<ROLE, X3><<<grid, WARPS * 32, P.total, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -537,6 +537,7 @@ int launch_role(const EdgeArgs& a, int* grid_out, cudaStream_t st) {
 
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* grid_out, cudaStream_t st) {
   if (a.n_mols <= 0) { if (grid_out) *grid_out = 0; return 0; }
+  if (edge_tc5_supported(d, role, a)) return launch_edge_tc5(role, a, grid_out, st);
   const bool x3 = d.precision == SMB_PREC_BF16X3;
   switch (role) {
     case ROLE_GATE: return x3 ? launch_role<ROLE_GATE, true>(a, grid_out, st) : launch_role<ROLE_GATE, false>(a, grid_out, st);

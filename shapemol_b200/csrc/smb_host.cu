@@ -47,6 +47,8 @@ EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
   e.ln_b = c.take(H * 4);
   e.w2 = gate ? c.take(H * 4) : c.take((size_t)(n2 / 8) * (H / 16) * 32 * fb);
   e.b2 = c.take((gate ? 4 : n2) * 4);
+  e.w1r_u = c.take((size_t)32 * H * 2);
+  e.w2_u = gate ? e.w1r_u : c.take((size_t)n2 * H * 2);
   return e;
 }
 NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2) {
@@ -233,6 +235,13 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
     } else {
       pack_frags(blob + e.w2, n2 / 8, H / 16, prec, [&](int n, int k) { return w2[(size_t)n * H + k]; });
       put(blob, e.b2, get(p + ".net.3.bias"), n2);
+      uint16_t* u1 = reinterpret_cast<uint16_t*>(blob + e.w1r_u);
+      for (int k = 0; k < kRbf; ++k)
+        for (int n = 0; n < H; ++n) u1[((size_t)(n / 8) * 512 + (size_t)k * 16 + (n % 8) * 2) / 2] = f2bf(w1[(size_t)n * ld1 + k]);
+      uint16_t* u2 = reinterpret_cast<uint16_t*>(blob + e.w2_u);
+      for (int n = 0; n < n2; ++n)
+        for (int k = 0; k < H; ++k)
+          u2[((size_t)(n / 8) * 2048 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2[(size_t)n * H + k]);
     }
   };
   pack_edge(L.gate, "refine_net.edge_pred_layer", 0, kRbf, true);

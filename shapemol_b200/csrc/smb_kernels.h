@@ -99,8 +99,13 @@ struct EdgeArgs {
   float* bn_partial;       // [gridDim.x*warps][32]
   // weights
   const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
+  const void* w1r_u; const void* w2_u;   // tcgen05 operand images (EdgeMlpOff::w1r_u / w2_u)
 };
-int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* grid_out, cudaStream_t st);
+// bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes
+int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
+// tcgen05 / TMEM implementation (smb_edge_tc5.cu): plain-bf16 mode, molecules of <= 32 atoms
+bool edge_tc5_supported(const smb_model_dims& d, int role, const EdgeArgs& a);
+int launch_edge_tc5(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 
 int launch_prep(const PrepArgs& a, cudaStream_t st);
 int launch_knn(const float* x, const int* mol_ptr, int n_mols, int k, int* nbr, int* deg, cudaStream_t st);

@@ -26,6 +26,9 @@ struct EdgeMlpOff {
   size_t ln_b;   // [H]
   size_t w2;     // B fragments [N2/8][H/16][32]   (gate: fp32 [H] vector)
   size_t b2;     // [N2] fp32
+  // tcgen05 (UMMA) operand images, bf16, no swizzle (smb_tc.cuh): used by the plain-bf16 edge kernels
+  size_t w1r_u;  // [32 k][H n] MN-major: byte(k, n) = (n/8)*512 + k*16 + (n%8)*2      (k >= 20 zero)
+  size_t w2_u;   // [N2 n][H k] K-major:  byte(n, k) = (n/8)*2048 + (k/8)*128 + (n%8)*16 + (k%8)*2
 };
 
 // Node-level chain: Y1 = X W1^T + b1 ; first n_pass columns are written out as they are, the last H
