@@ -98,11 +98,21 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   SMB_TIMED(SMB_PROF_KNN, launch_knn(x, b.mol_ptr, B, d.k, nbr, deg, st));
   if (io.nbr) SMB_CUDA_OK(cudaMemcpyAsync(io.nbr, nbr, (size_t)N * (d.k + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
 
+  // warp-specialised tcgen05 pipeline for the three attention roles (plain-bf16 mode, <= 32 atoms per molecule)
+  const bool ws = edge_ws_supported(d, n_max);
+  int4* tiles = wptr<int4>(ws_base, W.tiles + 16);
+  int* n_tiles = wptr<int>(ws_base, W.tiles);
+  if (ws) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
+  auto edge = [&](int role, const EdgeArgs& e, int* bn_rows) -> int {
+    return ws && role != ROLE_GATE ? launch_edge_ws(role, e, bn_rows, st) : launch_edge(d, role, e, bn_rows, st);
+  };
+
   EdgeArgs eb;
   memset(&eb, 0, sizeof(eb));
   eb.n_mols = B; eb.n_max = n_max; eb.k = d.k; eb.mol_ptr = b.mol_ptr; eb.x = x; eb.nbr = nbr; eb.deg = deg;
   eb.ab = ab; eb.q = q; eb.ew_in = ew; eb.ew_out = ew; eb.alpha = alpha; eb.agg = agg; eb.shape = io.shape; eb.vn = vn;
   eb.bn_partial = bn_part;
+  eb.abh = ab; eb.tiles = tiles; eb.n_tiles = n_tiles; eb.alpha_t = alpha;
 
   {  // global edge gate, computed once from the input coordinates (uni_transformer.py:507)
     EdgeArgs e = eb;
@@ -124,6 +134,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
+      if (ws) n.out1_h = reinterpret_cast<uint32_t*>(ab);
       fill_node_weights(n, blob, y.x2h_pre);
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
@@ -131,13 +142,13 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       EdgeArgs e = eb;
       e.col_a = 0; e.col_b = H;
       fill_edge_weights(e, blob, y.hk);
-      SMB_TIMED(SMB_PROF_EDGE_K, launch_edge(d, ROLE_K, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_K, edge(ROLE_K, e, nullptr));
     }
     {
       EdgeArgs e = eb;
       e.col_a = 2 * H; e.col_b = 3 * H;
       fill_edge_weights(e, blob, y.hv);
-      SMB_TIMED(SMB_PROF_EDGE_V, launch_edge(d, ROLE_V, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_V, edge(ROLE_V, e, nullptr));
     }
     {
       NodeArgs n = na;
@@ -151,6 +162,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
+      if (ws) n.out1_h = reinterpret_cast<uint32_t*>(ab);
       fill_node_weights(n, blob, y.h2x_pre);
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
@@ -158,7 +170,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       EdgeArgs e = eb;
       e.col_a = 0; e.col_b = H;
       fill_edge_weights(e, blob, y.xk);
-      SMB_TIMED(SMB_PROF_EDGE_K, launch_edge(d, ROLE_K, e, nullptr, st));
+      SMB_TIMED(SMB_PROF_EDGE_K, edge(ROLE_K, e, nullptr));
     }
     int bn_rows = 0;
     {
@@ -166,7 +178,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       e.col_a = 2 * H; e.col_b = 3 * H;
       e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
       fill_edge_weights(e, blob, y.xv);
-      SMB_TIMED(SMB_PROF_EDGE_XV, launch_edge(d, ROLE_XV, e, &bn_rows, st));
+      SMB_TIMED(SMB_PROF_EDGE_XV, edge(ROLE_XV, e, &bn_rows));
     }
     {
       BnArgs bn;

@@ -1,0 +1,727 @@
+// Warp-specialised tcgen05 / TMEM pipeline for the fused edge kernels (plain-bf16 contraction mode,
+// molecules of <= 32 atoms: the MOSES workload).  Same math as smb_edge_attn.cu / smb_edge_tc5.cu
+// (BaseX2HAttLayer / BaseH2XAttLayer, models/uni_transformer.py:48-162); this file changes the
+// SCHEDULE: one persistent CTA per SM, a static list of 128-row tiles, and five roles that hand tiles
+// to each other through mbarriers so that global-load latency, the two MMAs and the SIMT epilogues of
+// different tiles overlap.
+//
+// Tile = 128 edge rows = `nd` whole destination atoms of ONE molecule, `deg` rows each (the kNN
+// degree min(k, n-1) is the same for every atom of a molecule), built once per forward by
+// build_tiles_kernel.
+//
+//   warps 0-1   P     : two rows per thread.  neighbour index, |x_i - x_j|, 20 RBFs, one-hot(i), one-hot(j)
+//                       -> A1[128 x 96] bf16 in a 2-slot smem ring
+//   warp  18    MMA   : cp.async of the molecule's bf16 projection tiles (3-slot ring), then
+//                       GEMM1 (SS)  D[128 x 128] = A1 . [W1r ; A-tile ; B-tile]         (K = 96)
+//                       GEMM2       ROLE_K/XV (TS): D = z . W2^T, z from TMEM;  ROLE_V (SS): D^T = W2 . z^T
+//   warps 2-9   group 0 (even tiles), warps 10-17 group 1 (odd tiles): thread = (row, column half)
+//                 LN : D -> LayerNorm -> ReLU -> z (bf16; TMEM columns, or smem for ROLE_V)
+//                 E2 : ROLE_K  <Q_i, .> per head, softmax over the destination's rows, x gate -> alpha
+//                      ROLE_V  sum_j alpha (W2 z + b2), lane = channel, in-thread over the rows
+//                      ROLE_XV alpha w (x_i - x_j) -> VN linear maps -> BatchNorm partial sums
+//               while one group waits for its GEMM2 the other group's LayerNorm keeps the SM busy.
+//
+// TMEM (512 columns): D[3] at 0/128/256 (GEMM2 overwrites GEMM1's accumulator in place), z[2] at
+// 384/448.  alpha travels between the kernels in a tile-strided layout [tile][128 rows][16 heads].
+#include "smb_common.cuh"
+#include "smb_kernels.h"
+#include "smb_tc.cuh"
+
+#include <cstdlib>
+
+namespace smb {
+
+namespace {
+
+using namespace tc;
+
+constexpr int H = 128;
+constexpr int G = 32;                  // atoms per molecule supported by the one-hot operand
+constexpr int TM = 128;                // rows per tile
+constexpr int K1 = 32 + 2 * G;         // 96
+constexpr int A1_SBO = (K1 / 8) * 128; // 1536
+constexpr int A1_BYTES = TM * K1 * 2;  // 24576
+constexpr int AB_BYTES = 2 * G * H * 2;  // 16384: A-tile | B-tile, each [32 k][128 n] MN-major
+constexpr int LS = 17;                 // padded row stride of per-row head scratch
+constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
+constexpr int P_WARPS = 2, GRP_WARPS = 8, WARPS = 19, THREADS = WARPS * 32;   // 19 warps -> 96 registers per thread
+constexpr int MMA_WARP = 18;
+constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
+constexpr int GRP_THREADS = GRP_WARPS * 32;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t Z_COL = 384;
+
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_D1_FULL = 4, B_D2_FULL = 6, B_Z_FULL = 8, B_E2_DONE = 10, N_BARS = 12 };
+
+template <int ROLE>
+struct Plan {
+  static constexpr int o_bar = 0;                 // 12 mbarriers
+  static constexpr int o_tmem = 96;
+  static constexpr int o_vec = 128;               // ln_g | ln_b | b2   (3 x 128 floats)
+  static constexpr int o_w1r = o_vec + 1536;      // 8192
+  static constexpr int o_w2 = o_w1r + 8192;
+  static constexpr int w2_bytes = ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
+  static constexpr int o_a1 = o_w2 + w2_bytes;    // 2 slots
+  static constexpr int o_ab = o_a1 + 2 * A1_BYTES;   // 3 slots
+  static constexpr int o_grp = o_ab + 3 * AB_BYTES;
+  // per-group scratch
+  //  ROLE_K : q float[16][128] | logits float[128][17] | stat float2[2][128] | red float2[16][16] | ew float[128]
+  //  ROLE_V : z^T operand (32768) | alpha float[128][16] | stat | part float2[128]
+  //  ROLE_XV: alpha float[128][16] | w float[128][17] | rel float4[128] | o float[16][16][4] | stat | shape float[96]
+  static constexpr int g_q = 0;
+  static constexpr int g_z = 0;
+  static constexpr int g_alpha = ROLE == ROLE_V ? 32768 : 0;
+  static constexpr int g_log = 8192;                                   // ROLE_K logits / ROLE_XV w
+  static constexpr int g_stat = ROLE == ROLE_V ? 32768 + 8192 : ROLE == ROLE_K ? 8192 + 8704 : 8192 + 8704 + 2048 + 4096;
+  static constexpr int g_red = g_stat + 2048;                          // ROLE_K
+  static constexpr int g_ew = g_red + 2048;                            // ROLE_K
+  static constexpr int g_part = g_stat + 2048;                         // ROLE_V
+  static constexpr int g_rel = 8192 + 8704;                            // ROLE_XV
+  static constexpr int g_o = g_rel + 2048;                             // ROLE_XV
+  static constexpr int g_shape = g_stat + 2048;                        // ROLE_XV
+  static constexpr int grp_bytes = ROLE == ROLE_K ? g_ew + 512 : ROLE == ROLE_V ? g_part + 1024 : g_shape + 384;
+  static constexpr int o_vnw = o_grp + 2 * grp_bytes;                  // ROLE_XV: vn_feat | vn_dir
+  static constexpr int total = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);
+  static_assert(total <= 227 * 1024, "shared memory budget");
+  static_assert(grp_bytes % 16 == 0 && o_grp % 128 == 0, "alignment");
+};
+
+struct Tile {
+  int a0, mol, n, d0, nd, deg;
+  uint32_t recip;
+  __device__ __forceinline__ explicit Tile(const int4& t)
+      : a0(t.x), mol(t.y), n(t.z & 0xff), d0((t.z >> 8) & 0xff), nd((t.z >> 16) & 0xff), deg((t.z >> 24) & 0xff), recip((uint32_t)t.w) {}
+  __device__ __forceinline__ int rows() const { return nd * deg; }
+  __device__ __forceinline__ int dst_of(int r) const { return (int)(((uint32_t)r * recip) >> 16); }   // r / deg for r < 128
+};
+
+template <int ROLE>
+__global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
+  using P = Plan<ROLE>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::o_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::o_tmem);
+  float* s_g = reinterpret_cast<float*>(smem + P::o_vec);
+  float* s_be = s_g + H;
+  float* s_b2 = s_be + H;
+  unsigned char* s_w1r = smem + P::o_w1r;
+  unsigned char* s_w2 = smem + P::o_w2;
+  unsigned char* s_a1 = smem + P::o_a1;
+  unsigned char* s_ab = smem + P::o_ab;
+  float* s_vnw = reinterpret_cast<float*>(smem + P::o_vnw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KSTR = a.k + 1;
+  const int n_tiles = *a.n_tiles;
+  const int t_begin = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+  const int nt = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x) - t_begin;
+  const int4* tiles = a.tiles + t_begin;
+
+  // ---- once per CTA: weights -> smem, rings zeroed, TMEM allocation, mbarriers ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.w1r_u);
+    uint4* dst = reinterpret_cast<uint4*>(s_w1r);
+    for (int p = tid; p < 8192 / 16; p += THREADS) dst[p] = src[p];
+    const uint4* s2 = reinterpret_cast<const uint4*>(a.w2_u);
+    uint4* d2 = reinterpret_cast<uint4*>(s_w2);
+    for (int p = tid; p < P::w2_bytes / 16; p += THREADS) d2[p] = s2[p];
+    if (tid < H) {
+      s_g[tid] = a.ln_g[tid];
+      s_be[tid] = a.ln_b[tid];
+      s_b2[tid] = ROLE == ROLE_XV ? (tid < kHeads ? a.b2[tid] : 0.f) : a.b2[tid];
+    }
+    if (ROLE == ROLE_XV)
+      for (int p = tid; p < kHeads * kVnStride; p += THREADS) {
+        s_vnw[p] = a.vn_feat[p];
+        s_vnw[kHeads * kVnStride + p] = a.vn_dir[p];
+      }
+    // A1 and projection rings start at zero: rows / atoms that a tile does not use keep finite stale data
+    // that no one-hot column of a valid row selects
+    uint4* z0 = reinterpret_cast<uint4*>(s_a1);
+    for (int p = tid; p < (2 * A1_BYTES + 3 * AB_BYTES) / 16; p += THREADS) z0[p] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (tid == 32) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar + B_A1_FULL + b, P_WARPS * 32);
+      mbar_init(bar + B_A1_FREE + b, 1);
+      mbar_init(bar + B_D1_FULL + b, 1);
+      mbar_init(bar + B_D2_FULL + b, 1);
+      mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
+      mbar_init(bar + B_E2_DONE + b, GRP_THREADS);
+    }
+    mbar_init_fence();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < P_WARPS) {
+    // =====================================================================================
+    // P: A1 operand.  Row r of the tile is edge (i <- j): i = d0 + r / deg, slot s = r % deg.
+    // =====================================================================================
+    // thread `tid` builds rows tid and tid + 64
+    uint32_t old_i[2][P_ROWS], old_j[2][P_ROWS];   // byte offsets of the one-hot ones, per ring slot
+#pragma unroll
+    for (int u = 0; u < P_ROWS; ++u) { old_i[0][u] = old_i[1][u] = 4 * 128; old_j[0][u] = old_j[1][u] = 8 * 128; }
+    int4 td1 = nt > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
+    int4 td2 = nt > 1 ? __ldg(tiles + 1) : make_int4(0, 0, 0, 0);
+    int j1[P_ROWS];
+    auto fetch_j = [&](const Tile& N) {
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) {
+        const int r = tid + u * (P_WARPS * 32);
+        j1[u] = 0;
+        if (r < N.rows()) {
+          const int il = N.dst_of(r);
+          j1[u] = __ldg(a.nbr + (size_t)(N.a0 + N.d0 + il) * KSTR + (r - il * N.deg));
+        }
+      }
+    };
+    if (nt > 0) fetch_j(Tile(td1));
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      const Tile T(td1);
+      int j[P_ROWS];
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) j[u] = j1[u];
+      td1 = td2;
+      if (t + 2 < nt) td2 = __ldg(tiles + t + 2);
+      if (t + 1 < nt) fetch_j(Tile(td1));   // neighbour indices of the next tile (hides one of the two dependent loads)
+      const int slot = t & 1;
+      int i[P_ROWS];
+      float dist[P_ROWS];
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) {
+        const int r = tid + u * (P_WARPS * 32);
+        i[u] = 0; dist[u] = 0.f;
+        if (r < T.rows()) {
+          i[u] = T.d0 + T.dst_of(r);
+          const float* xi = a.x + (size_t)(T.a0 + i[u]) * 3;
+          const float* xj = a.x + (size_t)(T.a0 + j[u]) * 3;
+          const float rx = __ldg(xi) - __ldg(xj), ry = __ldg(xi + 1) - __ldg(xj + 1), rz = __ldg(xi + 2) - __ldg(xj + 2);
+          dist[u] = sqrtf(rx * rx + ry * ry + rz * rz);
+        }
+      }
+      if (t >= 2) mbar_wait(bar + B_A1_FREE + slot, ((t >> 1) - 1) & 1);
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) {
+        const int r = tid + u * (P_WARPS * 32);
+        if (r < T.rows()) {
+          unsigned char* arow = s_a1 + slot * A1_BYTES + (r >> 3) * A1_SBO + (r & 7) * 16;
+          float e[20];
+#pragma unroll
+          for (int q = 0; q < 20; ++q) {
+            const float dd = dist[u] - rbf_centre(q);
+            e[q] = exp2f(-0.72134752044448170f * dd * dd);
+          }
+          *reinterpret_cast<uint4*>(arow) = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+          *reinterpret_cast<uint4*>(arow + 128) =
+              make_uint4(pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
+          *reinterpret_cast<uint4*>(arow + 256) = make_uint4(pack_bf16(e[16], e[17]), pack_bf16(e[18], e[19]), 0u, 0u);
+          // one-hot(dst) in k = 32..63, one-hot(src) in k = 64..95: clear this row's previous one, set the new one
+          const uint32_t oi = (uint32_t)((4 + (i[u] >> 3)) * 128 + (i[u] & 7) * 2);
+          const uint32_t oj = (uint32_t)((8 + (j[u] >> 3)) * 128 + (j[u] & 7) * 2);
+          *reinterpret_cast<uint16_t*>(arow + (slot ? old_i[1][u] : old_i[0][u])) = 0;
+          *reinterpret_cast<uint16_t*>(arow + (slot ? old_j[1][u] : old_j[0][u])) = 0;
+          *reinterpret_cast<uint16_t*>(arow + oi) = 0x3F80;
+          *reinterpret_cast<uint16_t*>(arow + oj) = 0x3F80;
+          if (slot) { old_i[1][u] = oi; old_j[1][u] = oj; } else { old_i[0][u] = oi; old_j[0][u] = oj; }
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(bar + B_A1_FULL + slot);
+    }
+  } else if (warp < MMA_WARP) {
+    // =====================================================================================
+    // LayerNorm + role epilogue: group g owns tiles g, g+2, ...
+    // =====================================================================================
+    const int gw = warp - P_WARPS;           // 0..15
+    const int g = gw >> 3, half = (gw >> 2) & 1, qd = warp & 3;
+    const int r = qd * 32 + lane;            // TMEM lane = tile row (ROLE_V E2: output channel)
+    const int tg = (gw & 7) * 32 + lane;     // thread index inside the group
+    const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
+    unsigned char* gs = smem + P::o_grp + g * P::grp_bytes;
+    float2* s_stat = reinterpret_cast<float2*>(gs + P::g_stat);
+    float* s_log = reinterpret_cast<float*>(gs + P::g_log);             // ROLE_K logits, ROLE_XV w
+    float* s_q = reinterpret_cast<float*>(gs + P::g_q);                 // ROLE_K
+    float2* s_red = reinterpret_cast<float2*>(gs + P::g_red);           // ROLE_K
+    float* s_ew = reinterpret_cast<float*>(gs + P::g_ew);               // ROLE_K
+    unsigned char* s_z = gs + P::g_z;                                   // ROLE_V
+    float* s_al = reinterpret_cast<float*>(gs + P::g_alpha);            // ROLE_V / ROLE_XV
+    float2* s_part = reinterpret_cast<float2*>(gs + P::g_part);         // ROLE_V
+    float4* s_rel = reinterpret_cast<float4*>(gs + P::g_rel);           // ROLE_XV
+    float* s_o = reinterpret_cast<float*>(gs + P::g_o);                 // ROLE_XV
+    float* s_shape = reinterpret_cast<float*>(gs + P::g_shape);         // ROLE_XV
+    const int bar_id = 1 + g;
+    float bn_s = 0.f, bn_q = 0.f;   // ROLE_XV: per-warp BatchNorm partial sums (lane & 15 = channel, lanes < 16)
+
+    int4 td_next = g < nt ? __ldg(tiles + g) : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int t = g, it = 0; t < nt; t += 2, ++it) {
+      const Tile T(td_next);
+      if (t + 2 < nt) td_next = __ldg(tiles + t + 2);
+      const uint32_t ph = it & 1;
+      const uint32_t dcol = (uint32_t)(t % 3) * 128u;
+      const int rows = T.rows();
+      const bool valid = r < rows;
+      const int dl = min(T.dst_of(r), NDMAX - 1);
+      const int sl = r - dl * T.deg;
+
+      // ---- prefetch what the epilogue needs (lands while the LayerNorm runs) ----
+      float ew_r = 0.f;
+      float relx = 0.f, rely = 0.f, relz = 0.f;
+      if (ROLE == ROLE_K) {
+        const float* src = a.q + (size_t)(T.a0 + T.d0) * H;
+        for (int p = tg; p < T.nd * (H / 4); p += GRP_THREADS) cp_async16(s_q + p * 4, src + p * 4);
+        if (half == 0 && valid) ew_r = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
+      } else {
+        const float* src = a.alpha_t + (size_t)(t_begin + t) * (TM * kHeads);
+        for (int p = tg; p < TM * kHeads / 4; p += GRP_THREADS) cp_async16(s_al + p * 4, src + p * 4);
+      }
+      if (ROLE == ROLE_XV) {
+        if (tg < kShape * 3) s_shape[tg] = __ldg(a.shape + (size_t)T.mol * kShape * 3 + tg);
+        if (half == 0 && valid) {
+          const int i = T.d0 + dl;
+          const int j = __ldg(a.nbr + (size_t)(T.a0 + i) * KSTR + sl);
+          const float* xi = a.x + (size_t)(T.a0 + i) * 3;
+          const float* xj = a.x + (size_t)(T.a0 + j) * 3;
+          relx = __ldg(xi) - __ldg(xj); rely = __ldg(xi + 1) - __ldg(xj + 1); relz = __ldg(xi + 2) - __ldg(xj + 2);
+        }
+      }
+      cp_async_commit();
+
+      // =========================== LN: LayerNorm + ReLU -> z (bf16) ===========================
+      mbar_wait(bar + B_D1_FULL + g, ph);
+      fence_after_sync();
+      {
+        uint32_t v[64];
+        tmem_ld32(lane_addr + dcol + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(lane_addr + dcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        wait_ld();
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+          const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
+          s0 += f0; s1 += f1; s2 += f2; s3 += f3;
+          q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
+        }
+        const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
+        s_stat[half * TM + r] = make_float2(sum, sq);
+        named_sync(bar_id, GRP_THREADS);
+        const float2 ot = s_stat[(half ^ 1) * TM + r];
+        const float mean = (sum + ot.x) * (1.f / H);
+        const float var = fmaxf((sq + ot.y) * (1.f / H) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        const float shift = -mean * rstd;
+        // two passes of 32 columns keep the packed output at 16 registers
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          uint32_t zp[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const int c = hp * 32 + e;
+            const float4 gg = *reinterpret_cast<const float4*>(s_g + half * 64 + c);
+            const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + c);
+            const float y0 = fmaf(fmaf(__uint_as_float(v[c]), rstd, shift), gg.x, bb.x);
+            const float y1 = fmaf(fmaf(__uint_as_float(v[c + 1]), rstd, shift), gg.y, bb.y);
+            const float y2 = fmaf(fmaf(__uint_as_float(v[c + 2]), rstd, shift), gg.z, bb.z);
+            const float y3 = fmaf(fmaf(__uint_as_float(v[c + 3]), rstd, shift), gg.w, bb.w);
+            zp[e / 2] = pack_bf16_relu(y0, y1);
+            zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
+          }
+          if (ROLE == ROLE_V) {
+            // z^T operand: K-major [row][k]; this thread owns k = 64 half .. 64 half + 63 of row r
+            unsigned char* zrow = s_z + (r >> 3) * 2048 + (r & 7) * 16 + (half * 8 + hp * 4) * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(zrow + q * 128) = make_uint4(zp[4 * q], zp[4 * q + 1], zp[4 * q + 2], zp[4 * q + 3]);
+          } else {
+            tmem_st16(lane_addr + Z_COL + g * 64 + half * 32 + hp * 16, zp);
+          }
+        }
+        if (ROLE == ROLE_V) fence_async_smem();
+        else wait_st();
+      }
+      fence_before_sync();
+      mbar_arrive(bar + B_Z_FULL + g);
+
+      // =========================== E2 ===========================
+      mbar_wait(bar + B_D2_FULL + g, ph);
+      fence_after_sync();
+      cp_async_wait<0>();
+      if (ROLE == ROLE_XV && half == 0) s_rel[r] = make_float4(relx, rely, relz, 0.f);
+      if (ROLE == ROLE_K && half == 0) s_ew[r] = ew_r;
+      named_sync(bar_id, GRP_THREADS);   // staged q / alpha / shape / rel / ew visible to the group
+
+      if (ROLE == ROLE_K) {
+        float l[8];
+        {
+          uint32_t v[64];
+          tmem_ld32(lane_addr + dcol + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32(lane_addr + dcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          wait_ld();
+          fence_before_sync();
+          mbar_arrive(bar + B_E2_DONE + g);
+          // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
+          const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + half * 64);
+          const float scale = 0.35355339059327373f;   // 1/sqrt(dh), dh = 8
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) {
+            const float4 qa = qrow[2 * hh], qb = qrow[2 * hh + 1];
+            float acc = __uint_as_float(v[8 * hh]) * qa.x;
+            acc = fmaf(__uint_as_float(v[8 * hh + 1]), qa.y, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 2]), qa.z, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 3]), qa.w, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 4]), qb.x, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 5]), qb.y, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 6]), qb.z, acc);
+            acc = fmaf(__uint_as_float(v[8 * hh + 7]), qb.w, acc);
+            l[hh] = acc * scale;
+            s_log[r * LS + half * 8 + hh] = l[hh];
+          }
+        }
+        named_sync(bar_id, GRP_THREADS);
+        // per (destination, head): max and 1 / sum exp over the destination's rows; 4 threads share a pair
+        {
+          const int part = tg & 3;
+          for (int pair = tg >> 2; pair < T.nd * kHeads; pair += GRP_THREADS / 4) {
+            const int pd = pair >> 4, hd = pair & 15;
+            const float* col = s_log + (pd * T.deg) * LS + hd;
+            float mx = -INFINITY;
+            for (int q = part; q < T.deg; q += 4) mx = fmaxf(mx, col[q * LS]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float se = 0.f;
+            for (int q = part; q < T.deg; q += 4) se += __expf(col[q * LS] - mx);
+            se += __shfl_xor_sync(0xffffffffu, se, 1);
+            se += __shfl_xor_sync(0xffffffffu, se, 2);
+            if (part == 0) s_red[pair] = make_float2(mx, 1.f / se);
+          }
+        }
+        named_sync(bar_id, GRP_THREADS);
+        {
+          const float ew = s_ew[r];
+          float o[8];
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) {
+            const float2 mi = s_red[dl * kHeads + half * 8 + hh];
+            o[hh] = __expf(l[hh] - mi.x) * mi.y * ew;
+          }
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(a.alpha_t + ((size_t)(t_begin + t) * TM + r) * kHeads + half * 8);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      } else if (ROLE == ROLE_V) {
+        // thread = output channel c (TMEM lane), columns = edge rows; this half covers rows [64 half, 64 half + 64)
+        const int c = r, hq = c >> 3;
+        const float b2c = s_b2[c];
+        if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
+          if (half == 0) a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
+          fence_before_sync();
+          mbar_arrive(bar + B_E2_DONE + g);
+        } else {
+          const int c0 = half * 64;
+          int di = (int)(((uint32_t)c0 * T.recip) >> 16);   // destination of this half's first row
+          int cnt = c0 - di * T.deg;                        // rows of it that belong to the other half
+          const bool straddle = half == 1 && cnt > 0 && rows > 64;
+          bool first = straddle;
+          float acc = 0.f, asum = 0.f, first_acc = 0.f, first_asum = 0.f;
+          int first_i = -1;
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            const int col0 = c0 + ch * 32;
+            if (col0 >= rows) break;
+            uint32_t v[32];
+            tmem_ld32(lane_addr + dcol + col0, v);
+            wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int rr = col0 + q;
+              if (rr < rows) {
+                const float al = s_al[rr * 16 + hq];
+                acc = fmaf(al, __uint_as_float(v[q]), acc);
+                asum += al;
+                if (++cnt == T.deg) {
+                  if (first) {
+                    first_i = di; first_acc = acc; first_asum = asum; first = false;
+                  } else {
+                    a.agg[(size_t)(T.a0 + T.d0 + di) * H + c] = fmaf(b2c, asum, acc);
+                  }
+                  acc = 0.f; asum = 0.f; cnt = 0; ++di;
+                }
+              }
+            }
+          }
+          fence_before_sync();
+          mbar_arrive(bar + B_E2_DONE + g);
+          if (half == 0) s_part[c] = make_float2(acc, asum);   // rows of a destination that continues in the other half
+          named_sync(bar_id, GRP_THREADS);
+          if (first_i >= 0) {
+            const float2 pp = s_part[c];
+            a.agg[(size_t)(T.a0 + T.d0 + first_i) * H + c] = fmaf(b2c, first_asum + pp.y, first_acc + pp.x);
+          }
+        }
+      } else {   // ROLE_XV
+        if (half == 0) {
+          uint32_t v[16];
+          tmem_ld16(lane_addr + dcol, v);
+          wait_ld();
+          if (valid) {
+            const float4* al = reinterpret_cast<const float4*>(s_al + r * kHeads);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 av = al[q];
+              s_log[r * LS + 4 * q] = av.x * (__uint_as_float(v[4 * q]) + s_b2[4 * q]);
+              s_log[r * LS + 4 * q + 1] = av.y * (__uint_as_float(v[4 * q + 1]) + s_b2[4 * q + 1]);
+              s_log[r * LS + 4 * q + 2] = av.z * (__uint_as_float(v[4 * q + 2]) + s_b2[4 * q + 2]);
+              s_log[r * LS + 4 * q + 3] = av.w * (__uint_as_float(v[4 * q + 3]) + s_b2[4 * q + 3]);
+            }
+          }
+        }
+        fence_before_sync();
+        mbar_arrive(bar + B_E2_DONE + g);
+        named_sync(bar_id, GRP_THREADS);
+        // o_i^a = sum_j alpha e_w w (x_i - x_j)
+        for (int p = tg; p < T.nd * kHeads; p += GRP_THREADS) {
+          const int pd = p >> 4, hd = p & 15;
+          const int r0 = pd * T.deg;
+          float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll 4
+          for (int q = 0; q < T.deg; ++q) {
+            const float w = s_log[(r0 + q) * LS + hd];
+            const float4 rl = s_rel[r0 + q];
+            ox = fmaf(w, rl.x, ox); oy = fmaf(w, rl.y, oy); oz = fmaf(w, rl.z, oz);
+          }
+          float* o = s_o + (pd * kHeads + hd) * 4;
+          o[0] = ox; o[1] = oy; o[2] = oz;
+        }
+        named_sync(bar_id, GRP_THREADS);
+        // VN linear maps (shape_vn_layers.py:100,105): lanes 0..15 map_to_feat channel, 16..31 map_to_dir channel
+        for (int pd = gw & 7; pd < T.nd; pd += GRP_WARPS) {
+          const int ch = lane & 15, which = lane >> 4;
+          const float* w = s_vnw + (which * kHeads + ch) * kVnStride;
+          const float* so = s_o + pd * kHeads * 4;
+          const float* xp = a.x + (size_t)(T.a0 + T.d0 + pd) * 3;
+          const float xi = __ldg(xp), yi = __ldg(xp + 1), zi = __ldg(xp + 2);
+          float vx = w[0] * xi, vy = w[0] * yi, vz = w[0] * zi;
+#pragma unroll
+          for (int cc = 0; cc < kHeads; ++cc) {
+            const float wc = w[1 + cc];
+            vx = fmaf(wc, so[cc * 4], vx); vy = fmaf(wc, so[cc * 4 + 1], vy); vz = fmaf(wc, so[cc * 4 + 2], vz);
+          }
+#pragma unroll 8
+          for (int cc = 0; cc < kShape; ++cc) {
+            const float wc = w[1 + kHeads + cc];
+            vx = fmaf(wc, s_shape[cc * 3], vx); vy = fmaf(wc, s_shape[cc * 3 + 1], vy); vz = fmaf(wc, s_shape[cc * 3 + 2], vz);
+          }
+          float* row = a.vn + (size_t)(T.a0 + T.d0 + pd) * kVnRow;
+          row[3 + which * 48 + ch * 3] = vx; row[4 + which * 48 + ch * 3] = vy; row[5 + which * 48 + ch * 3] = vz;
+          if (lane < 3) {
+            float sm = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < kHeads; ++cc) sm += so[cc * 4 + lane];
+            row[lane] = sm * (1.f / kHeads);
+          }
+          if (which == 0) {
+            const float nu = sqrtf(vx * vx + vy * vy + vz * vz) + 1e-6f;
+            bn_s += nu; bn_q = fmaf(nu, nu, bn_q);
+          }
+        }
+      }
+      // the group's scratch is reused two tiles later; every path above ends behind a group barrier
+      // except the last stage, which the LayerNorm barrier of the next tile orders
+      named_sync(bar_id, GRP_THREADS);
+    }   // tiles
+    if (ROLE == ROLE_XV && lane < 16) {
+      float* part = a.bn_partial + (size_t)(blockIdx.x * (2 * GRP_WARPS) + gw) * 32;
+      part[lane] = bn_s;
+      part[16 + lane] = bn_q;
+    }
+  } else {
+    // =====================================================================================
+    // MMA issuer + projection-tile loader (one warp; lane 0 issues the MMAs)
+    // =====================================================================================
+    const int pa = a.col_a / H, pb = a.col_b / H;
+    auto load_ab = [&](int t) {
+      if (t < nt) {
+        const Tile T(__ldg(tiles + t));
+        unsigned char* dst = s_ab + (t % 3) * AB_BYTES;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.abh) + (size_t)T.a0 * (4 * H * 2);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const int pcol = (part ? pb : pa) * (H * 2);
+          for (int ab = 0; ab < T.n; ab += 8) {
+            const int atom = ab + (lane & 7);
+            if (atom < T.n) {
+#pragma unroll
+              for (int cg = 0; cg < 4; ++cg) {
+                const int chunk = cg * 4 + (lane >> 3);
+                cp_async16(dst + part * (G * H * 2) + chunk * 512 + atom * 16, src + (size_t)atom * (4 * H * 2) + pcol + chunk * 16);
+              }
+            }
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    constexpr uint32_t IDESC1 = idesc_bf16(H, true);
+    constexpr uint32_t IDESC2 = idesc_bf16(ROLE == ROLE_XV ? kHeads : H, false);
+    const uint32_t a1_base = smem_u32(s_a1), ab_base = smem_u32(s_ab), w1r_base = smem_u32(s_w1r), w2_base = smem_u32(s_w2);
+    load_ab(0);
+    load_ab(1);
+#pragma unroll 1
+    for (int t = 0; t <= nt; ++t) {
+      if (t < nt) {
+        mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
+        if (t >= 3) mbar_wait(bar + B_E2_DONE + ((t - 3) & 1), ((t - 3) >> 1) & 1);
+        cp_async_wait<1>();
+        fence_async_smem();
+        __syncwarp();
+        fence_after_sync();
+        if (lane == 0) {
+          const uint32_t d = tmem + (uint32_t)(t % 3) * 128u;
+          const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
+          const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
+          const uint32_t b1[3] = {w1r_base, ab, ab + G * H * 2};
+#pragma unroll
+          for (int ks = 0; ks < K1 / 16; ++ks)
+            mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(b1[ks >> 1] + (ks & 1) * 256, 128, 512), IDESC1, ks > 0);
+          mma_commit(bar + B_A1_FREE + (t & 1));
+          mma_commit(bar + B_D1_FULL + (t & 1));
+        }
+        __syncwarp();
+      }
+      if (t >= 1) {
+        const int u = t - 1, g = u & 1;
+        mbar_wait(bar + B_Z_FULL + g, (u >> 1) & 1);
+        fence_after_sync();
+        if (lane == 0) {
+          const uint32_t d = tmem + (uint32_t)(u % 3) * 128u;
+          if (ROLE == ROLE_V) {
+            const uint32_t zt = smem_u32(smem + P::o_grp + g * P::grp_bytes + P::g_z);
+#pragma unroll
+            for (int ks = 0; ks < H / 16; ++ks)
+              mma_ss(d, smem_desc(w2_base + ks * 256, 128, 2048), smem_desc(zt + ks * 256, 128, 2048), IDESC2, ks > 0);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < H / 16; ++ks)
+              mma_ts(d, tmem + Z_COL + g * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
+          }
+          mma_commit(bar + B_D2_FULL + g);
+        }
+        __syncwarp();
+      }
+      load_ab(t + 2);   // slot (t + 2) % 3 was read by GEMM1(t - 1), complete since z_full(t - 1)
+    }
+    cp_async_wait<0>();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<TMEM_COLS>(tmem);
+}
+
+// ---- static tile list -------------------------------------------------------------------------------
+__device__ __forceinline__ int tiles_of(int n, int k) {
+  if (n <= 0) return 0;
+  const int deg = min(k, n - 1);
+  if (deg == 0) return 1;
+  const int per = TM / deg;
+  return (n + per - 1) / per;
+}
+
+__global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict__ mol_ptr, int n_mols, int k, int4* __restrict__ tiles,
+                                                           int* __restrict__ n_tiles) {
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_thread = (n_mols + 1023) / 1024;
+  const int m0 = min(n_mols, tid * per_thread), m1 = min(n_mols, m0 + per_thread);
+  int cnt = 0;
+  for (int m = m0; m < m1; ++m) cnt += tiles_of(mol_ptr[m + 1] - mol_ptr[m], k);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += up;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += up;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  int off = inc - cnt + (warp > 0 ? s_warp[warp - 1] : 0);
+  if (tid == 1023) *n_tiles = s_warp[31];
+  for (int m = m0; m < m1; ++m) {
+    const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
+    if (n <= 0) continue;
+    const int deg = min(k, n - 1);
+    const int per = deg > 0 ? TM / deg : 1;
+    const int recip = deg > 0 ? 65536 / deg + 1 : 0;
+    for (int d0 = 0; d0 < n; d0 += per) {
+      const int nd = min(per, n - d0);
+      tiles[off++] = make_int4(a0, m, n | (d0 << 8) | (nd << 16) | (deg << 24), recip);
+    }
+  }
+}
+
+int g_sms = 0;
+int sms() {
+  if (g_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_sms = n;
+    else
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+template <int ROLE>
+int launch_ws(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(edge_ws_kernel<ROLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<ROLE>::total);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int grid = sms();
+  if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
+  if (bn_rows_out) *bn_rows_out = grid * 2 * GRP_WARPS;
+  edge_ws_kernel<ROLE><<<grid, THREADS, Plan<ROLE>::total, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+bool edge_ws_supported(const smb_model_dims& d, int n_max) {
+  static const bool off = getenv("SMB_EDGE_TC5") != nullptr || getenv("SMB_EDGE_LEGACY") != nullptr;   // debugging aids
+  return !off && d.precision == SMB_PREC_BF16 && d.hidden == H && n_max >= 1 && n_max <= G && d.k >= 1;
+}
+
+int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st) {
+  build_tiles_kernel<<<1, 1024, 0, st>>>(mol_ptr, n_mols, k, tiles, n_tiles);
+  return (int)cudaGetLastError();
+}
+
+int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
+  switch (role) {
+    case ROLE_K: return launch_ws<ROLE_K>(a, bn_rows_out, st);
+    case ROLE_V: return launch_ws<ROLE_V>(a, bn_rows_out, st);
+    case ROLE_XV: return launch_ws<ROLE_XV>(a, bn_rows_out, st);
+    default: set_error_msg("launch_edge_ws: unsupported role"); return SMB_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace smb

@@ -112,7 +112,11 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.nbr = c.take(n * KS * 4);
   w.deg = c.take(n * 4);
   w.ew = c.take(n * KS * 4);
-  w.alpha = c.take(n * KS * kHeads * 4);
+  w.max_tiles = (int)(n / 4 + b + 8);
+  {  // alpha: [N][k+1][16] (atom-strided kernels) or [tile][128][16] (warp-specialised pipeline)
+    const size_t by_atom = n * KS * kHeads * 4, by_tile = (size_t)w.max_tiles * 128 * kHeads * 4;
+    w.alpha = c.take(by_atom > by_tile ? by_atom : by_tile);
+  }
   w.x = c.take(n * 3 * 4);
   w.h_a = c.take(n * H * 4);
   w.h_b = c.take(n * H * 4);
@@ -123,6 +127,7 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.bn_part_rows = kEdgeMaxCtas * kEdgeWarps;
   w.bn_part = c.take((size_t)w.bn_part_rows * 32 * 4);
   w.bn_param = c.take(32 * 4);
+  w.tiles = c.take(16 + (size_t)w.max_tiles * 16);
   w.total = c.off;
   return w;
 }

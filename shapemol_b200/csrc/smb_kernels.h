@@ -73,6 +73,7 @@ struct NodeArgs {
   const void* w2; const float* b2;
   const float* residual;   // optional [N][n2]
   float* out1;             // [N][n_pass]
+  uint32_t* out1_h;        // optional: the pass-through columns as packed bf16 pairs [N][n_pass/2] instead of out1
   float* out2;             // [N][n2_valid]
 };
 int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);
@@ -100,12 +101,22 @@ struct EdgeArgs {
   // weights
   const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
   const void* w1r_u; const void* w2_u;   // tcgen05 operand images (EdgeMlpOff::w1r_u / w2_u)
+  // warp-specialised pipeline (smb_edge_ws.cu)
+  const void* abh;         // [N][4H] bf16: the node projections as written by node_mlp_kernel (out1_h)
+  const int4* tiles;       // static tile list (build_tiles_kernel)
+  const int* n_tiles;
+  float* alpha_t;          // [tile][128 rows][16 heads]  (ROLE_K out; ROLE_V / ROLE_XV in)
 };
 // bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 // tcgen05 / TMEM implementation (smb_edge_tc5.cu): plain-bf16 mode, molecules of <= 32 atoms
 bool edge_tc5_supported(const smb_model_dims& d, int role, const EdgeArgs& a);
 int launch_edge_tc5(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
+
+// warp-specialised tcgen05 pipeline (smb_edge_ws.cu): plain-bf16 mode, molecules of <= 32 atoms, all three roles together
+bool edge_ws_supported(const smb_model_dims& d, int n_max);
+int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st);
+int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 
 int launch_prep(const PrepArgs& a, cudaStream_t st);
 int launch_knn(const float* x, const int* mol_ptr, int n_mols, int k, int* nbr, int* deg, cudaStream_t st);

@@ -157,8 +157,13 @@ __global__ void __launch_bounds__(256, 1) node_mlp_kernel(NodeArgs a) {
     for (int nt = 0; nt < NT_CHUNK; ++nt) {
       const int col = pc * 64 + nt * 8 + 2 * t;
       const float2 bb = *reinterpret_cast<const float2*>(a.b1 + col);
-      if (ok0) *reinterpret_cast<float2*>(a.out1 + (size_t)row0 * a.n_pass + col) = make_float2(c[nt][0] + bb.x, c[nt][1] + bb.y);
-      if (ok1) *reinterpret_cast<float2*>(a.out1 + (size_t)row1 * a.n_pass + col) = make_float2(c[nt][2] + bb.x, c[nt][3] + bb.y);
+      if (a.out1_h) {   // bf16 pairs for the tcgen05 edge pipeline (which rounds these operands to bf16 anyway)
+        if (ok0) a.out1_h[((size_t)row0 * a.n_pass + col) >> 1] = pack_bf16x2(c[nt][0] + bb.x, c[nt][1] + bb.y);
+        if (ok1) a.out1_h[((size_t)row1 * a.n_pass + col) >> 1] = pack_bf16x2(c[nt][2] + bb.x, c[nt][3] + bb.y);
+      } else {
+        if (ok0) *reinterpret_cast<float2*>(a.out1 + (size_t)row0 * a.n_pass + col) = make_float2(c[nt][0] + bb.x, c[nt][1] + bb.y);
+        if (ok1) *reinterpret_cast<float2*>(a.out1 + (size_t)row1 * a.n_pass + col) = make_float2(c[nt][2] + bb.x, c[nt][3] + bb.y);
+      }
     }
     __syncthreads();
   }
