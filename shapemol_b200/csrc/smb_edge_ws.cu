@@ -11,7 +11,7 @@
 //
 //   warps 0-1   P     : two rows per thread.  neighbour index, |x_i - x_j|, 20 RBFs, one-hot(i), one-hot(j)
 //                       -> A1[128 x 96] bf16 in a 2-slot smem ring
-//   warp  18    MMA   : cp.async of the molecule's bf16 projection tiles (3-slot ring), then
+//   warp  18/19 MMA   : (18: loader + GEMM1, 19: GEMM2) cp.async of the molecule's bf16 projection tiles (3-slot ring), then
 //                       GEMM1 (SS)  D[128 x 128] = A1 . [W1r ; A-tile ; B-tile]         (K = 96)
 //                       GEMM2       ROLE_K/XV (TS): D = z . W2^T, z from TMEM;  ROLE_V (SS): D^T = W2 . z^T
 //   warps 2-9   group 0 (even tiles), warps 10-17 group 1 (odd tiles): thread = (row, column half)
@@ -44,47 +44,51 @@ constexpr int A1_BYTES = TM * K1 * 2;  // 24576
 constexpr int AB_BYTES = 2 * G * H * 2;  // 16384: A-tile | B-tile, each [32 k][128 n] MN-major
 constexpr int LS = 17;                 // padded row stride of per-row head scratch
 constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
-constexpr int P_WARPS = 2, GRP_WARPS = 8, WARPS = 19, THREADS = WARPS * 32;   // 19 warps -> 96 registers per thread
-constexpr int MMA_WARP = 18;
+constexpr int P_WARPS = 2, GRP_WARPS = 8, WARPS = 20, THREADS = WARPS * 32;   // 20 warps -> 96 registers per thread
+constexpr int LN_WARP0 = P_WARPS, E2_WARP0 = LN_WARP0 + GRP_WARPS, MMA_WARP = E2_WARP0 + GRP_WARPS;
+constexpr int BAR_LN = 1, BAR_E2 = 2;   // named barriers (0 is __syncthreads)
 constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
 constexpr int GRP_THREADS = GRP_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t Z_COL = 384;
 
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_D1_FULL = 4, B_D2_FULL = 6, B_Z_FULL = 8, B_E2_DONE = 10, N_BARS = 12 };
+// mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 9, B_E2_DONE = 12, N_BARS = 15 };
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 12 mbarriers
-  static constexpr int o_tmem = 96;
+  static constexpr int o_bar = 0;                 // 15 mbarriers
+  static constexpr int o_tmem = 120;
   static constexpr int o_vec = 128;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
   static constexpr int w2_bytes = ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
   static constexpr int o_a1 = o_w2 + w2_bytes;    // 2 slots
   static constexpr int o_ab = o_a1 + 2 * A1_BYTES;   // 3 slots
-  static constexpr int o_grp = o_ab + 3 * AB_BYTES;
-  // per-group scratch
-  //  ROLE_K : q float[16][128] | logits float[128][17] | stat float2[2][128] | red float2[16][16] | ew float[128]
-  //  ROLE_V : z^T operand (32768) | alpha float[128][16] | stat | part float2[128]
-  //  ROLE_XV: alpha float[128][16] | w float[128][17] | rel float4[128] | o float[16][16][4] | stat | shape float[96]
-  static constexpr int g_q = 0;
-  static constexpr int g_z = 0;
-  static constexpr int g_alpha = ROLE == ROLE_V ? 32768 : 0;
-  static constexpr int g_log = 8192;                                   // ROLE_K logits / ROLE_XV w
-  static constexpr int g_stat = ROLE == ROLE_V ? 32768 + 8192 : ROLE == ROLE_K ? 8192 + 8704 : 8192 + 8704 + 2048 + 4096;
-  static constexpr int g_red = g_stat + 2048;                          // ROLE_K
-  static constexpr int g_ew = g_red + 2048;                            // ROLE_K
-  static constexpr int g_part = g_stat + 2048;                         // ROLE_V
-  static constexpr int g_rel = 8192 + 8704;                            // ROLE_XV
-  static constexpr int g_o = g_rel + 2048;                             // ROLE_XV
-  static constexpr int g_shape = g_stat + 2048;                        // ROLE_XV
-  static constexpr int grp_bytes = ROLE == ROLE_K ? g_ew + 512 : ROLE == ROLE_V ? g_part + 1024 : g_shape + 384;
-  static constexpr int o_vnw = o_grp + 2 * grp_bytes;                  // ROLE_XV: vn_feat | vn_dir
+  static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float2[2 buffers][2 halves][128]
+  static constexpr int o_z = o_stat + 4096;          // ROLE_V: z^T operand, 2 x 32768
+  static constexpr int o_e2 = o_z + (ROLE == ROLE_V ? 2 * TM * H * 2 : 0);
+  // E2 scratch: two staging slots (ROLE_K: q float[16][128]; ROLE_V: alpha float[128][16]; ROLE_XV: alpha | shape float[96])
+  static constexpr int stage_bytes = ROLE == ROLE_XV ? 8192 + 384 : 8192;
+  static constexpr int e_stage = 0;
+  static constexpr int e_log = 2 * stage_bytes;       // ROLE_K logits / ROLE_XV w : float[128][17]
+  static constexpr int e_red = e_log + 8704;          // ROLE_K float2[16][16]
+  static constexpr int e_ew = e_red + 2048;           // ROLE_K float[128]
+  static constexpr int e_part = 2 * stage_bytes;      // ROLE_V float2[128]
+  static constexpr int e_rel = e_log + 8704;          // ROLE_XV float4[128]
+  static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[16][16][4]
+  static constexpr int e2_bytes = ROLE == ROLE_K ? e_ew + 512 : ROLE == ROLE_V ? e_part + 1024 : e_o + 4096;
+  static constexpr int o_vnw = o_e2 + e2_bytes;       // ROLE_XV: vn_feat | vn_dir
   static constexpr int total = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);
   static_assert(total <= 227 * 1024, "shared memory budget");
-  static_assert(grp_bytes % 16 == 0 && o_grp % 128 == 0, "alignment");
+  static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0, "alignment");
 };
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct Tile {
   int a0, mol, n, d0, nd, deg;
@@ -145,9 +149,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar + B_A1_FULL + b, P_WARPS * 32);
       mbar_init(bar + B_A1_FREE + b, 1);
+      mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
+    }
+    for (int b = 0; b < 3; ++b) {
       mbar_init(bar + B_D1_FULL + b, 1);
       mbar_init(bar + B_D2_FULL + b, 1);
-      mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
       mbar_init(bar + B_E2_DONE + b, GRP_THREADS);
     }
     mbar_init_fence();
@@ -162,49 +168,61 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     // =====================================================================================
     // P: A1 operand.  Row r of the tile is edge (i <- j): i = d0 + r / deg, slot s = r % deg.
     // =====================================================================================
-    // thread `tid` builds rows tid and tid + 64
+    // thread `tid` builds rows tid and tid + 64.  Three-deep software pipeline: while tile t is written, the
+    // coordinates of tile t + 1, the neighbour indices of tile t + 2 and the descriptor of tile t + 3 are in flight.
     uint32_t old_i[2][P_ROWS], old_j[2][P_ROWS];   // byte offsets of the one-hot ones, per ring slot
 #pragma unroll
     for (int u = 0; u < P_ROWS; ++u) { old_i[0][u] = old_i[1][u] = 4 * 128; old_j[0][u] = old_j[1][u] = 8 * 128; }
-    int4 td1 = nt > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
-    int4 td2 = nt > 1 ? __ldg(tiles + 1) : make_int4(0, 0, 0, 0);
-    int j1[P_ROWS];
-    auto fetch_j = [&](const Tile& N) {
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 td_a = nt > 0 ? __ldg(tiles) : zero4, td_b = nt > 1 ? __ldg(tiles + 1) : zero4, td_c = nt > 2 ? __ldg(tiles + 2) : zero4;
+    int j_a[P_ROWS], j_b[P_ROWS];
+    float xr[P_ROWS][6];
+    auto fetch_j = [&](const Tile& N, int (&j)[P_ROWS]) {
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = tid + u * (P_WARPS * 32);
-        j1[u] = 0;
+        j[u] = 0;
         if (r < N.rows()) {
           const int il = N.dst_of(r);
-          j1[u] = __ldg(a.nbr + (size_t)(N.a0 + N.d0 + il) * KSTR + (r - il * N.deg));
+          j[u] = __ldg(a.nbr + (size_t)(N.a0 + N.d0 + il) * KSTR + (r - il * N.deg));
         }
       }
     };
-    if (nt > 0) fetch_j(Tile(td1));
+    auto fetch_x = [&](const Tile& N, const int (&j)[P_ROWS]) {
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) {
+        const int r = tid + u * (P_WARPS * 32);
+        if (r < N.rows()) {
+          const float* xi = a.x + (size_t)(N.a0 + N.d0 + N.dst_of(r)) * 3;
+          const float* xj = a.x + (size_t)(N.a0 + j[u]) * 3;
+          xr[u][0] = __ldg(xi); xr[u][1] = __ldg(xi + 1); xr[u][2] = __ldg(xi + 2);
+          xr[u][3] = __ldg(xj); xr[u][4] = __ldg(xj + 1); xr[u][5] = __ldg(xj + 2);
+        }
+      }
+    };
+    if (nt > 0) { fetch_j(Tile(td_a), j_a); fetch_x(Tile(td_a), j_a); }
+    if (nt > 1) fetch_j(Tile(td_b), j_b);
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
-      const Tile T(td1);
-      int j[P_ROWS];
-#pragma unroll
-      for (int u = 0; u < P_ROWS; ++u) j[u] = j1[u];
-      td1 = td2;
-      if (t + 2 < nt) td2 = __ldg(tiles + t + 2);
-      if (t + 1 < nt) fetch_j(Tile(td1));   // neighbour indices of the next tile (hides one of the two dependent loads)
+      const Tile T(td_a);
       const int slot = t & 1;
-      int i[P_ROWS];
+      int i[P_ROWS], j[P_ROWS];
       float dist[P_ROWS];
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = tid + u * (P_WARPS * 32);
-        i[u] = 0; dist[u] = 0.f;
-        if (r < T.rows()) {
-          i[u] = T.d0 + T.dst_of(r);
-          const float* xi = a.x + (size_t)(T.a0 + i[u]) * 3;
-          const float* xj = a.x + (size_t)(T.a0 + j[u]) * 3;
-          const float rx = __ldg(xi) - __ldg(xj), ry = __ldg(xi + 1) - __ldg(xj + 1), rz = __ldg(xi + 2) - __ldg(xj + 2);
-          dist[u] = sqrtf(rx * rx + ry * ry + rz * rz);
-        }
+        j[u] = j_a[u];
+        i[u] = T.d0 + T.dst_of(r);
+        const float rx = xr[u][0] - xr[u][3], ry = xr[u][1] - xr[u][4], rz = xr[u][2] - xr[u][5];
+        dist[u] = sqrtf(rx * rx + ry * ry + rz * rz);
       }
+      // next loads (consumed one / two / three iterations from now)
+      td_a = td_b; td_b = td_c;
+#pragma unroll
+      for (int u = 0; u < P_ROWS; ++u) j_a[u] = j_b[u];
+      if (t + 1 < nt) fetch_x(Tile(td_a), j_a);
+      if (t + 2 < nt) fetch_j(Tile(td_b), j_b);
+      if (t + 3 < nt) td_c = __ldg(tiles + t + 3);
       if (t >= 2) mbar_wait(bar + B_A1_FREE + slot, ((t >> 1) - 1) & 1);
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
           for (int q = 0; q < 20; ++q) {
             const float dd = dist[u] - rbf_centre(q);
-            e[q] = exp2f(-0.72134752044448170f * dd * dd);
+            e[q] = fast_ex2(-0.72134752044448170f * dd * dd);
           }
           *reinterpret_cast<uint4*>(arow) = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
           *reinterpret_cast<uint4*>(arow + 128) =
@@ -234,127 +252,150 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       fence_async_smem();
       mbar_arrive(bar + B_A1_FULL + slot);
     }
+  } else if (warp < E2_WARP0) {
+    // =====================================================================================
+    // LN: D -> LayerNorm -> ReLU -> z (bf16).  thread = (row, column half); every tile.
+    // =====================================================================================
+    const int gw = warp - LN_WARP0;
+    const int half = gw >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
+    float2* s_stat = reinterpret_cast<float2*>(smem + P::o_stat);
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      const int b3 = t % 3, zb = t & 1;
+      mbar_wait(bar + B_D1_FULL + b3, (t / 3) & 1);
+      fence_after_sync();
+      uint32_t v[64];
+      tmem_ld32(lane_addr + b3 * 128 + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(lane_addr + b3 * 128 + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      wait_ld();
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 64; e += 4) {
+        const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
+        s0 += f0; s1 += f1; s2 += f2; s3 += f3;
+        q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
+      }
+      const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
+      float2* st = s_stat + zb * (2 * TM);          // double-buffered: a fast thread may already be one tile ahead
+      st[half * TM + r] = make_float2(sum, sq);
+      named_sync(BAR_LN, GRP_THREADS);
+      const float2 ot = st[(half ^ 1) * TM + r];
+      const float mean = (sum + ot.x) * (1.f / H);
+      const float var = fmaxf((sq + ot.y) * (1.f / H) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float shift = -mean * rstd;
+      // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
+      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % 3, ((t - 2) / 3) & 1);
+      // two passes of 32 columns keep the packed output at 16 registers
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        uint32_t zp[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const int c = hp * 32 + e;
+          const float4 gg = *reinterpret_cast<const float4*>(s_g + half * 64 + c);
+          const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + c);
+          const float y0 = fmaf(fmaf(__uint_as_float(v[c]), rstd, shift), gg.x, bb.x);
+          const float y1 = fmaf(fmaf(__uint_as_float(v[c + 1]), rstd, shift), gg.y, bb.y);
+          const float y2 = fmaf(fmaf(__uint_as_float(v[c + 2]), rstd, shift), gg.z, bb.z);
+          const float y3 = fmaf(fmaf(__uint_as_float(v[c + 3]), rstd, shift), gg.w, bb.w);
+          zp[e / 2] = pack_bf16_relu(y0, y1);
+          zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
+        }
+        if (ROLE == ROLE_V) {
+          // z^T operand: K-major [row][k]; this thread owns k = 64 half .. 64 half + 63 of row r
+          unsigned char* zrow = smem + P::o_z + zb * (TM * H * 2) + (r >> 3) * 2048 + (r & 7) * 16 + (half * 8 + hp * 4) * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(zrow + q * 128) = make_uint4(zp[4 * q], zp[4 * q + 1], zp[4 * q + 2], zp[4 * q + 3]);
+        } else {
+          tmem_st16(lane_addr + Z_COL + zb * 64 + half * 32 + hp * 16, zp);
+        }
+      }
+      if (ROLE == ROLE_V) fence_async_smem();
+      else wait_st();
+      fence_before_sync();
+      mbar_arrive(bar + B_Z_FULL + zb);
+    }
   } else if (warp < MMA_WARP) {
     // =====================================================================================
-    // LayerNorm + role epilogue: group g owns tiles g, g+2, ...
+    // E2: role epilogue on GEMM2's accumulator.  thread = (row, column half); every tile.
     // =====================================================================================
-    const int gw = warp - P_WARPS;           // 0..15
-    const int g = gw >> 3, half = (gw >> 2) & 1, qd = warp & 3;
-    const int r = qd * 32 + lane;            // TMEM lane = tile row (ROLE_V E2: output channel)
-    const int tg = (gw & 7) * 32 + lane;     // thread index inside the group
+    const int gw = warp - E2_WARP0;
+    const int half = gw >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;            // TMEM lane = tile row (ROLE_V: output channel)
+    const int tg = gw * 32 + lane;           // thread index inside the role
     const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
-    unsigned char* gs = smem + P::o_grp + g * P::grp_bytes;
-    float2* s_stat = reinterpret_cast<float2*>(gs + P::g_stat);
-    float* s_log = reinterpret_cast<float*>(gs + P::g_log);             // ROLE_K logits, ROLE_XV w
-    float* s_q = reinterpret_cast<float*>(gs + P::g_q);                 // ROLE_K
-    float2* s_red = reinterpret_cast<float2*>(gs + P::g_red);           // ROLE_K
-    float* s_ew = reinterpret_cast<float*>(gs + P::g_ew);               // ROLE_K
-    unsigned char* s_z = gs + P::g_z;                                   // ROLE_V
-    float* s_al = reinterpret_cast<float*>(gs + P::g_alpha);            // ROLE_V / ROLE_XV
-    float2* s_part = reinterpret_cast<float2*>(gs + P::g_part);         // ROLE_V
-    float4* s_rel = reinterpret_cast<float4*>(gs + P::g_rel);           // ROLE_XV
-    float* s_o = reinterpret_cast<float*>(gs + P::g_o);                 // ROLE_XV
-    float* s_shape = reinterpret_cast<float*>(gs + P::g_shape);         // ROLE_XV
-    const int bar_id = 1 + g;
+    unsigned char* es = smem + P::o_e2;
+    float* s_log = reinterpret_cast<float*>(es + P::e_log);             // ROLE_K logits, ROLE_XV w
+    float2* s_red = reinterpret_cast<float2*>(es + P::e_red);           // ROLE_K
+    float* s_ew = reinterpret_cast<float*>(es + P::e_ew);               // ROLE_K
+    float2* s_part = reinterpret_cast<float2*>(es + P::e_part);         // ROLE_V
+    float4* s_rel = reinterpret_cast<float4*>(es + P::e_rel);           // ROLE_XV
+    float* s_o = reinterpret_cast<float*>(es + P::e_o);                 // ROLE_XV
     float bn_s = 0.f, bn_q = 0.f;   // ROLE_XV: per-warp BatchNorm partial sums (lane & 15 = channel, lanes < 16)
 
-    int4 td_next = g < nt ? __ldg(tiles + g) : make_int4(0, 0, 0, 0);
-#pragma unroll 1
-    for (int t = g, it = 0; t < nt; t += 2, ++it) {
-      const Tile T(td_next);
-      if (t + 2 < nt) td_next = __ldg(tiles + t + 2);
-      const uint32_t ph = it & 1;
-      const uint32_t dcol = (uint32_t)(t % 3) * 128u;
-      const int rows = T.rows();
-      const bool valid = r < rows;
-      const int dl = min(T.dst_of(r), NDMAX - 1);
-      const int sl = r - dl * T.deg;
-
-      // ---- prefetch what the epilogue needs (lands while the LayerNorm runs) ----
-      float ew_r = 0.f;
-      float relx = 0.f, rely = 0.f, relz = 0.f;
+    // what tile `t` needs from global memory, staged one tile ahead: q rows / alpha tile / shape (cp.async,
+    // slot t & 1) and this thread's gate value / relative position (registers)
+    float pre_ew = 0.f, pre_x = 0.f, pre_y = 0.f, pre_z = 0.f;
+    auto stage = [&](int t, const Tile& T) {
+      unsigned char* slot = es + P::e_stage + (t & 1) * P::stage_bytes;
+      const int dl = min(T.dst_of(r), NDMAX - 1), sl = r - dl * T.deg;
+      const bool valid = r < T.rows();
       if (ROLE == ROLE_K) {
         const float* src = a.q + (size_t)(T.a0 + T.d0) * H;
-        for (int p = tg; p < T.nd * (H / 4); p += GRP_THREADS) cp_async16(s_q + p * 4, src + p * 4);
-        if (half == 0 && valid) ew_r = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
+        float* dst = reinterpret_cast<float*>(slot);
+        for (int p = tg; p < T.nd * (H / 4); p += GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        pre_ew = 0.f;
+        if (half == 0 && valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
       } else {
         const float* src = a.alpha_t + (size_t)(t_begin + t) * (TM * kHeads);
-        for (int p = tg; p < TM * kHeads / 4; p += GRP_THREADS) cp_async16(s_al + p * 4, src + p * 4);
+        float* dst = reinterpret_cast<float*>(slot);
+        for (int p = tg; p < TM * kHeads / 4; p += GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
       }
       if (ROLE == ROLE_XV) {
-        if (tg < kShape * 3) s_shape[tg] = __ldg(a.shape + (size_t)T.mol * kShape * 3 + tg);
+        if (tg < kShape * 3 / 4) cp_async16(slot + TM * kHeads * 4 + tg * 16, a.shape + (size_t)T.mol * kShape * 3 + tg * 4);
+        pre_x = pre_y = pre_z = 0.f;
         if (half == 0 && valid) {
           const int i = T.d0 + dl;
           const int j = __ldg(a.nbr + (size_t)(T.a0 + i) * KSTR + sl);
           const float* xi = a.x + (size_t)(T.a0 + i) * 3;
           const float* xj = a.x + (size_t)(T.a0 + j) * 3;
-          relx = __ldg(xi) - __ldg(xj); rely = __ldg(xi + 1) - __ldg(xj + 1); relz = __ldg(xi + 2) - __ldg(xj + 2);
+          pre_x = __ldg(xi) - __ldg(xj); pre_y = __ldg(xi + 1) - __ldg(xj + 1); pre_z = __ldg(xi + 2) - __ldg(xj + 2);
         }
       }
+    };
+
+    int4 td_cur = nt > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
+    int4 td_nx = nt > 1 ? __ldg(tiles + 1) : make_int4(0, 0, 0, 0);
+    if (nt > 0) stage(0, Tile(td_cur));
+    cp_async_commit();
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      const Tile T(td_cur);
+      const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
+      td_cur = td_nx;
+      if (t + 2 < nt) td_nx = __ldg(tiles + t + 2);
+      if (t + 1 < nt) stage(t + 1, Tile(td_cur));   // slot (t + 1) & 1: its readers (tile t - 1) are behind the trailing barrier
       cp_async_commit();
+      const int b3 = t % 3;
+      const uint32_t dcol = (uint32_t)b3 * 128u;
+      const int rows = T.rows();
+      const bool valid = r < rows;
+      const int dl = min(T.dst_of(r), NDMAX - 1);
+      const unsigned char* slot = es + P::e_stage + (t & 1) * P::stage_bytes;
+      const float* s_q = reinterpret_cast<const float*>(slot);            // ROLE_K
+      const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV
+      const float* s_shape = reinterpret_cast<const float*>(slot + TM * kHeads * 4);   // ROLE_XV
 
-      // =========================== LN: LayerNorm + ReLU -> z (bf16) ===========================
-      mbar_wait(bar + B_D1_FULL + g, ph);
-      fence_after_sync();
-      {
-        uint32_t v[64];
-        tmem_ld32(lane_addr + dcol + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld32(lane_addr + dcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        wait_ld();
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-        for (int e = 0; e < 64; e += 4) {
-          const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
-          s0 += f0; s1 += f1; s2 += f2; s3 += f3;
-          q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
-        }
-        const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
-        s_stat[half * TM + r] = make_float2(sum, sq);
-        named_sync(bar_id, GRP_THREADS);
-        const float2 ot = s_stat[(half ^ 1) * TM + r];
-        const float mean = (sum + ot.x) * (1.f / H);
-        const float var = fmaxf((sq + ot.y) * (1.f / H) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + 1e-5f);
-        const float shift = -mean * rstd;
-        // two passes of 32 columns keep the packed output at 16 registers
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          uint32_t zp[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const int c = hp * 32 + e;
-            const float4 gg = *reinterpret_cast<const float4*>(s_g + half * 64 + c);
-            const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + c);
-            const float y0 = fmaf(fmaf(__uint_as_float(v[c]), rstd, shift), gg.x, bb.x);
-            const float y1 = fmaf(fmaf(__uint_as_float(v[c + 1]), rstd, shift), gg.y, bb.y);
-            const float y2 = fmaf(fmaf(__uint_as_float(v[c + 2]), rstd, shift), gg.z, bb.z);
-            const float y3 = fmaf(fmaf(__uint_as_float(v[c + 3]), rstd, shift), gg.w, bb.w);
-            zp[e / 2] = pack_bf16_relu(y0, y1);
-            zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
-          }
-          if (ROLE == ROLE_V) {
-            // z^T operand: K-major [row][k]; this thread owns k = 64 half .. 64 half + 63 of row r
-            unsigned char* zrow = s_z + (r >> 3) * 2048 + (r & 7) * 16 + (half * 8 + hp * 4) * 128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(zrow + q * 128) = make_uint4(zp[4 * q], zp[4 * q + 1], zp[4 * q + 2], zp[4 * q + 3]);
-          } else {
-            tmem_st16(lane_addr + Z_COL + g * 64 + half * 32 + hp * 16, zp);
-          }
-        }
-        if (ROLE == ROLE_V) fence_async_smem();
-        else wait_st();
-      }
-      fence_before_sync();
-      mbar_arrive(bar + B_Z_FULL + g);
-
-      // =========================== E2 ===========================
-      mbar_wait(bar + B_D2_FULL + g, ph);
-      fence_after_sync();
-      cp_async_wait<0>();
+      cp_async_wait<1>();                      // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV && half == 0) s_rel[r] = make_float4(relx, rely, relz, 0.f);
       if (ROLE == ROLE_K && half == 0) s_ew[r] = ew_r;
-      named_sync(bar_id, GRP_THREADS);   // staged q / alpha / shape / rel / ew visible to the group
+      mbar_wait(bar + B_D2_FULL + b3, (t / 3) & 1);
+      fence_after_sync();
+      named_sync(BAR_E2, GRP_THREADS);         // staged q / alpha / shape / rel / ew visible to the role
 
       if (ROLE == ROLE_K) {
         float l[8];
@@ -364,10 +405,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           tmem_ld32(lane_addr + dcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           wait_ld();
           fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + g);
+          mbar_arrive(bar + B_E2_DONE + b3);
           // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
           const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + half * 64);
-          const float scale = 0.35355339059327373f;   // 1/sqrt(dh), dh = 8
+          const float scale = 0.35355339059327373f * 1.4426950408889634f;   // 1/sqrt(dh) (dh = 8) x log2(e): softmax in base 2
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const float4 qa = qrow[2 * hh], qb = qrow[2 * hh + 1];
@@ -383,32 +424,40 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
             s_log[r * LS + half * 8 + hh] = l[hh];
           }
         }
-        named_sync(bar_id, GRP_THREADS);
-        // per (destination, head): max and 1 / sum exp over the destination's rows; 4 threads share a pair
+        named_sync(BAR_E2, GRP_THREADS);
+        // per (destination, head): max and 1 / sum exp2 over the destination's rows; 4 threads share a pair,
+        // each holds <= 8 of the <= 32 rows in registers
         {
           const int part = tg & 3;
           for (int pair = tg >> 2; pair < T.nd * kHeads; pair += GRP_THREADS / 4) {
             const int pd = pair >> 4, hd = pair & 15;
             const float* col = s_log + (pd * T.deg) * LS + hd;
+            float lv[8];
             float mx = -INFINITY;
-            for (int q = part; q < T.deg; q += 4) mx = fmaxf(mx, col[q * LS]);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const int q = part + 4 * qq;
+              lv[qq] = q < T.deg ? col[q * LS] : -INFINITY;
+              mx = fmaxf(mx, lv[qq]);
+            }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             float se = 0.f;
-            for (int q = part; q < T.deg; q += 4) se += __expf(col[q * LS] - mx);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) se += fast_ex2(lv[qq] - mx);
             se += __shfl_xor_sync(0xffffffffu, se, 1);
             se += __shfl_xor_sync(0xffffffffu, se, 2);
             if (part == 0) s_red[pair] = make_float2(mx, 1.f / se);
           }
         }
-        named_sync(bar_id, GRP_THREADS);
+        named_sync(BAR_E2, GRP_THREADS);
         {
           const float ew = s_ew[r];
           float o[8];
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const float2 mi = s_red[dl * kHeads + half * 8 + hh];
-            o[hh] = __expf(l[hh] - mi.x) * mi.y * ew;
+            o[hh] = fast_ex2(l[hh] - mi.x) * (mi.y * ew);
           }
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(a.alpha_t + ((size_t)(t_begin + t) * TM + r) * kHeads + half * 8);
@@ -423,48 +472,49 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
           if (half == 0) a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
           fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + g);
+          mbar_arrive(bar + B_E2_DONE + b3);
         } else {
-          const int c0 = half * 64;
-          int di = (int)(((uint32_t)c0 * T.recip) >> 16);   // destination of this half's first row
-          int cnt = c0 - di * T.deg;                        // rows of it that belong to the other half
-          const bool straddle = half == 1 && cnt > 0 && rows > 64;
-          bool first = straddle;
-          float acc = 0.f, asum = 0.f, first_acc = 0.f, first_asum = 0.f;
-          int first_i = -1;
-#pragma unroll 1
-          for (int ch = 0; ch < 2; ++ch) {
-            const int col0 = c0 + ch * 32;
-            if (col0 >= rows) break;
-            uint32_t v[32];
-            tmem_ld32(lane_addr + dcol + col0, v);
+          // this half owns the destinations pd = half, half + 2, ...: their deg <= 31 columns are read in
+          // power-of-two pieces, so the sum over a destination's rows is a branch-free in-thread loop
+          const float* al0 = s_al + hq;
+          for (int pd = half; pd < T.nd; pd += 2) {
+            const int col = pd * T.deg;
+            const uint32_t ta = lane_addr + dcol + col;
+            uint32_t v16[16], v8[8], v4[4], v2[2], v1[1];
+            int o = 0;
+            if (T.deg & 16) { tmem_ld16(ta, v16); o = 16; }
+            if (T.deg & 8) { tmem_ld8(ta + o, v8); o += 8; }
+            if (T.deg & 4) { tmem_ld4(ta + o, v4); o += 4; }
+            if (T.deg & 2) { tmem_ld2(ta + o, v2); o += 2; }
+            if (T.deg & 1) tmem_ld1(ta + o, v1);
             wait_ld();
+            const float* al = al0 + col * kHeads;
+            float acc = 0.f, asum = 0.f;
+            if (T.deg & 16) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const int rr = col0 + q;
-              if (rr < rows) {
-                const float al = s_al[rr * 16 + hq];
-                acc = fmaf(al, __uint_as_float(v[q]), acc);
-                asum += al;
-                if (++cnt == T.deg) {
-                  if (first) {
-                    first_i = di; first_acc = acc; first_asum = asum; first = false;
-                  } else {
-                    a.agg[(size_t)(T.a0 + T.d0 + di) * H + c] = fmaf(b2c, asum, acc);
-                  }
-                  acc = 0.f; asum = 0.f; cnt = 0; ++di;
-                }
-              }
+              for (int q = 0; q < 16; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v16[q]), acc); asum += w; }
+              al += 16 * kHeads;
             }
+            if (T.deg & 8) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v8[q]), acc); asum += w; }
+              al += 8 * kHeads;
+            }
+            if (T.deg & 4) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v4[q]), acc); asum += w; }
+              al += 4 * kHeads;
+            }
+            if (T.deg & 2) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v2[q]), acc); asum += w; }
+              al += 2 * kHeads;
+            }
+            if (T.deg & 1) { const float w = al[0]; acc = fmaf(w, __uint_as_float(v1[0]), acc); asum += w; }
+            a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, asum, acc);
           }
           fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + g);
-          if (half == 0) s_part[c] = make_float2(acc, asum);   // rows of a destination that continues in the other half
-          named_sync(bar_id, GRP_THREADS);
-          if (first_i >= 0) {
-            const float2 pp = s_part[c];
-            a.agg[(size_t)(T.a0 + T.d0 + first_i) * H + c] = fmaf(b2c, first_asum + pp.y, first_acc + pp.x);
-          }
+          mbar_arrive(bar + B_E2_DONE + b3);
         }
       } else {   // ROLE_XV
         if (half == 0) {
@@ -484,8 +534,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           }
         }
         fence_before_sync();
-        mbar_arrive(bar + B_E2_DONE + g);
-        named_sync(bar_id, GRP_THREADS);
+        mbar_arrive(bar + B_E2_DONE + b3);
+        named_sync(BAR_E2, GRP_THREADS);
         // o_i^a = sum_j alpha e_w w (x_i - x_j)
         for (int p = tg; p < T.nd * kHeads; p += GRP_THREADS) {
           const int pd = p >> 4, hd = p & 15;
@@ -500,9 +550,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           float* o = s_o + (pd * kHeads + hd) * 4;
           o[0] = ox; o[1] = oy; o[2] = oz;
         }
-        named_sync(bar_id, GRP_THREADS);
+        named_sync(BAR_E2, GRP_THREADS);
         // VN linear maps (shape_vn_layers.py:100,105): lanes 0..15 map_to_feat channel, 16..31 map_to_dir channel
-        for (int pd = gw & 7; pd < T.nd; pd += GRP_WARPS) {
+        for (int pd = gw; pd < T.nd; pd += GRP_WARPS) {
           const int ch = lane & 15, which = lane >> 4;
           const float* w = s_vnw + (which * kHeads + ch) * kVnStride;
           const float* so = s_o + pd * kHeads * 4;
@@ -533,23 +583,22 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           }
         }
       }
-      // the group's scratch is reused two tiles later; every path above ends behind a group barrier
-      // except the last stage, which the LayerNorm barrier of the next tile orders
-      named_sync(bar_id, GRP_THREADS);
+      named_sync(BAR_E2, GRP_THREADS);   // scratch and the staging slots are reused by the next tiles
     }   // tiles
+    cp_async_wait<0>();
     if (ROLE == ROLE_XV && lane < 16) {
-      float* part = a.bn_partial + (size_t)(blockIdx.x * (2 * GRP_WARPS) + gw) * 32;
+      float* part = a.bn_partial + (size_t)(blockIdx.x * GRP_WARPS + gw) * 32;
       part[lane] = bn_s;
       part[16 + lane] = bn_q;
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     // =====================================================================================
-    // MMA issuer + projection-tile loader (one warp; lane 0 issues the MMAs)
+    // GEMM1 issuer + projection-tile loader (lane 0 issues the MMAs)
     // =====================================================================================
     const int pa = a.col_a / H, pb = a.col_b / H;
-    auto load_ab = [&](int t) {
+    auto load_ab = [&](int t, const int4& td) {
       if (t < nt) {
-        const Tile T(__ldg(tiles + t));
+        const Tile T(td);
         unsigned char* dst = s_ab + (t % 3) * AB_BYTES;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.abh) + (size_t)T.a0 * (4 * H * 2);
 #pragma unroll
@@ -570,55 +619,65 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       cp_async_commit();
     };
     constexpr uint32_t IDESC1 = idesc_bf16(H, true);
-    constexpr uint32_t IDESC2 = idesc_bf16(ROLE == ROLE_XV ? kHeads : H, false);
-    const uint32_t a1_base = smem_u32(s_a1), ab_base = smem_u32(s_ab), w1r_base = smem_u32(s_w1r), w2_base = smem_u32(s_w2);
-    load_ab(0);
-    load_ab(1);
+    const uint32_t a1_base = smem_u32(s_a1), ab_base = smem_u32(s_ab), w1r_base = smem_u32(s_w1r);
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    load_ab(0, nt > 0 ? __ldg(tiles) : zero4);
+    load_ab(1, nt > 1 ? __ldg(tiles + 1) : zero4);
+    int4 td_nx = nt > 2 ? __ldg(tiles + 2) : zero4;   // descriptor of tile t + 2, loaded one iteration early
 #pragma unroll 1
-    for (int t = 0; t <= nt; ++t) {
-      if (t < nt) {
-        mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
-        if (t >= 3) mbar_wait(bar + B_E2_DONE + ((t - 3) & 1), ((t - 3) >> 1) & 1);
-        cp_async_wait<1>();
-        fence_async_smem();
-        __syncwarp();
-        fence_after_sync();
-        if (lane == 0) {
-          const uint32_t d = tmem + (uint32_t)(t % 3) * 128u;
-          const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
-          const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
-          const uint32_t b1[3] = {w1r_base, ab, ab + G * H * 2};
+    for (int t = 0; t < nt; ++t) {
+      const int4 td_ld = td_nx;
+      if (t + 3 < nt) td_nx = __ldg(tiles + t + 3);
+      mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
+      if (t >= 3) mbar_wait(bar + B_E2_DONE + t % 3, (t / 3 - 1) & 1);   // tile t - 3 left D[t % 3]
+      cp_async_wait<1>();
+      fence_async_smem();
+      __syncwarp();
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t d = tmem + (uint32_t)(t % 3) * 128u;
+        const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
+        const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
+        const uint32_t b1[3] = {w1r_base, ab, ab + G * H * 2};
 #pragma unroll
-          for (int ks = 0; ks < K1 / 16; ++ks)
-            mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(b1[ks >> 1] + (ks & 1) * 256, 128, 512), IDESC1, ks > 0);
-          mma_commit(bar + B_A1_FREE + (t & 1));
-          mma_commit(bar + B_D1_FULL + (t & 1));
-        }
-        __syncwarp();
+        for (int ks = 0; ks < K1 / 16; ++ks)
+          mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(b1[ks >> 1] + (ks & 1) * 256, 128, 512), IDESC1, ks > 0);
+        mma_commit(bar + B_A1_FREE + (t & 1));
+        mma_commit(bar + B_D1_FULL + t % 3);
       }
-      if (t >= 1) {
-        const int u = t - 1, g = u & 1;
-        mbar_wait(bar + B_Z_FULL + g, (u >> 1) & 1);
-        fence_after_sync();
-        if (lane == 0) {
-          const uint32_t d = tmem + (uint32_t)(u % 3) * 128u;
-          if (ROLE == ROLE_V) {
-            const uint32_t zt = smem_u32(smem + P::o_grp + g * P::grp_bytes + P::g_z);
-#pragma unroll
-            for (int ks = 0; ks < H / 16; ++ks)
-              mma_ss(d, smem_desc(w2_base + ks * 256, 128, 2048), smem_desc(zt + ks * 256, 128, 2048), IDESC2, ks > 0);
-          } else {
-#pragma unroll
-            for (int ks = 0; ks < H / 16; ++ks)
-              mma_ts(d, tmem + Z_COL + g * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
-          }
-          mma_commit(bar + B_D2_FULL + g);
-        }
-        __syncwarp();
-      }
-      load_ab(t + 2);   // slot (t + 2) % 3 was read by GEMM1(t - 1), complete since z_full(t - 1)
+      __syncwarp();
+      // projection slot (t + 2) % 3 was read by GEMM1(t - 1)
+      if (t >= 1) mbar_wait(bar + B_A1_FREE + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+      load_ab(t + 2, td_ld);
     }
     cp_async_wait<0>();
+  } else {
+    // =====================================================================================
+    // GEMM2 issuer
+    // =====================================================================================
+    constexpr uint32_t IDESC2 = idesc_bf16(ROLE == ROLE_XV ? kHeads : H, false);
+    const uint32_t w2_base = smem_u32(s_w2);
+#pragma unroll 1
+    for (int u = 0; u < nt; ++u) {
+      const int zb = u & 1;
+      mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t d = tmem + (uint32_t)(u % 3) * 128u;
+        if (ROLE == ROLE_V) {
+          const uint32_t zt = smem_u32(smem + P::o_z + zb * (TM * H * 2));
+#pragma unroll
+          for (int ks = 0; ks < H / 16; ++ks)
+            mma_ss(d, smem_desc(w2_base + ks * 256, 128, 2048), smem_desc(zt + ks * 256, 128, 2048), IDESC2, ks > 0);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < H / 16; ++ks)
+            mma_ts(d, tmem + Z_COL + zb * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
+        }
+        mma_commit(bar + B_D2_FULL + u % 3);
+      }
+      __syncwarp();
+    }
   }
 
   fence_before_sync();
@@ -698,7 +757,7 @@ int launch_ws(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
   }
   int grid = sms();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
-  if (bn_rows_out) *bn_rows_out = grid * 2 * GRP_WARPS;
+  if (bn_rows_out) *bn_rows_out = grid * GRP_WARPS;
   edge_ws_kernel<ROLE><<<grid, THREADS, Plan<ROLE>::total, st>>>(a);
   return (int)cudaGetLastError();
 }
