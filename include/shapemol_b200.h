@@ -182,6 +182,10 @@ SMB_API int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batc
                        void* stream);
 
 /* t[b] -= 1 on the device (keeps the sampling loop free of host syncs / graph-capturable). */
+/* Debug aid (timing experiments, SMB_WS_DBG & 16): clock64 stamps [8 events][128 tiles] of CTA 0 of the last
+ * warp-specialised edge kernel.  Not part of the reference-facing surface. */
+SMB_API int smb_debug_ws_trace(int64_t* host_out);
+
 SMB_API int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream);
 
 /* ---- VN-DGCNN shape encoder ---------------------------------------------------------------------

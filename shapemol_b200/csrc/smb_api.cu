@@ -134,7 +134,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
-      if (ws) n.out1_h = reinterpret_cast<uint32_t*>(ab);
+      if (ws) { n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr; }
       fill_node_weights(n, blob, y.x2h_pre);
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
@@ -162,7 +162,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
-      if (ws) n.out1_h = reinterpret_cast<uint32_t*>(ab);
+      if (ws) { n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr; }
       fill_node_weights(n, blob, y.h2x_pre);
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
@@ -273,6 +273,8 @@ int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batch, const
   if (rc > 0) smb::set_error("posterior_kernel launch", (cudaError_t)rc);
   return rc;
 }
+
+int smb_debug_ws_trace(int64_t* host_out) { return smb::debug_ws_trace(reinterpret_cast<long long*>(host_out)); }
 
 int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream) {
   if (n_mols > 0 && !t) { smb::set_error_msg("smb_decrement_t: null pointer"); return SMB_E_BADARG; }

@@ -53,13 +53,13 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t Z_COL = 384;
 
 // mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 9, B_E2_DONE = 12, N_BARS = 15 };
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 9, B_E2_DONE = 12, B_AB_FULL = 15, N_BARS = 18 };
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 15 mbarriers
-  static constexpr int o_tmem = 120;
-  static constexpr int o_vec = 128;               // ln_g | ln_b | b2   (3 x 128 floats)
+  static constexpr int o_bar = 0;                 // 18 mbarriers
+  static constexpr int o_tmem = 144;
+  static constexpr int o_vec = 256;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
   static constexpr int w2_bytes = ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
@@ -98,6 +98,11 @@ struct Tile {
   __device__ __forceinline__ int rows() const { return nd * deg; }
   __device__ __forceinline__ int dst_of(int r) const { return (int)(((uint32_t)r * recip) >> 16); }   // r / deg for r < 128
 };
+
+// timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
+constexpr int TRACE_EVENTS = 12, TRACE_TILES = 128;
+__device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
+#define SMB_TRACE(ev, t, cond) do { if ((a.dbg & 16) && (a.dbg >> 8) == ROLE && blockIdx.x == 0 && (t) < TRACE_TILES && (cond)) g_trace[ev][t] = clock64(); } while (0)
 
 template <int ROLE>
 __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       mbar_init(bar + B_D1_FULL + b, 1);
       mbar_init(bar + B_D2_FULL + b, 1);
       mbar_init(bar + B_E2_DONE + b, GRP_THREADS);
+      mbar_init(bar + B_AB_FULL + b, 1);
     }
     mbar_init_fence();
   }
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = tid + u * (P_WARPS * 32);
-        if (r < T.rows()) {
+        if (r < T.rows() && !((a.dbg & 4) && t >= 2)) {
           unsigned char* arow = s_a1 + slot * A1_BYTES + (r >> 3) * A1_SBO + (r & 7) * 16;
           float e[20];
 #pragma unroll
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
       }
       fence_async_smem();
+      SMB_TRACE(0, t, tid == 0);
       mbar_arrive(bar + B_A1_FULL + slot);
     }
   } else if (warp < E2_WARP0) {
@@ -266,11 +273,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const int b3 = t % 3, zb = t & 1;
       mbar_wait(bar + B_D1_FULL + b3, (t / 3) & 1);
       fence_after_sync();
+      SMB_TRACE(2, t, gw == 0 && lane == 0);
       uint32_t v[64];
       tmem_ld32(lane_addr + b3 * 128 + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(lane_addr + b3 * 128 + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       wait_ld();
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      if (!(a.dbg & 2))
 #pragma unroll
       for (int e = 0; e < 64; e += 4) {
         const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
@@ -289,6 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
       if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % 3, ((t - 2) / 3) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
+      if (!(a.dbg & 2))
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
         uint32_t zp[16];
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (ROLE == ROLE_V) fence_async_smem();
       else wait_st();
       fence_before_sync();
+      SMB_TRACE(3, t, gw == 0 && lane == 0);
       mbar_arrive(bar + B_Z_FULL + zb);
     }
   } else if (warp < MMA_WARP) {
@@ -395,7 +406,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (ROLE == ROLE_K && half == 0) s_ew[r] = ew_r;
       mbar_wait(bar + B_D2_FULL + b3, (t / 3) & 1);
       fence_after_sync();
+      SMB_TRACE(5, t, tg == 0);
       named_sync(BAR_E2, GRP_THREADS);         // staged q / alpha / shape / rel / ew visible to the role
+      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); named_sync(BAR_E2, GRP_THREADS); continue; }
 
       if (ROLE == ROLE_K) {
         float l[8];
@@ -583,6 +596,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           }
         }
       }
+      SMB_TRACE(6, t, tg == 0);
       named_sync(BAR_E2, GRP_THREADS);   // scratch and the staging slots are reused by the next tiles
     }   // tiles
     cp_async_wait<0>();
@@ -595,62 +609,61 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     // =====================================================================================
     // GEMM1 issuer + projection-tile loader (lane 0 issues the MMAs)
     // =====================================================================================
+    // projection tiles of tile t's molecule: two bulk copies (dst part | src part, n * 256 bytes each) into slot t % 3,
+    // in the MN-major operand layout with an n * 16-byte column-group stride (written like that by node_mlp_kernel)
     const int pa = a.col_a / H, pb = a.col_b / H;
     auto load_ab = [&](int t, const int4& td) {
-      if (t < nt) {
+      if (t < nt && lane == 0) {
         const Tile T(td);
         unsigned char* dst = s_ab + (t % 3) * AB_BYTES;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.abh) + (size_t)T.a0 * (4 * H * 2);
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          const int pcol = (part ? pb : pa) * (H * 2);
-          for (int ab = 0; ab < T.n; ab += 8) {
-            const int atom = ab + (lane & 7);
-            if (atom < T.n) {
-#pragma unroll
-              for (int cg = 0; cg < 4; ++cg) {
-                const int chunk = cg * 4 + (lane >> 3);
-                cp_async16(dst + part * (G * H * 2) + chunk * 512 + atom * 16, src + (size_t)atom * (4 * H * 2) + pcol + chunk * 16);
-              }
-            }
-          }
-        }
+        const uint32_t bytes = (uint32_t)T.n * (H * 2);
+        uint64_t* fb = bar + B_AB_FULL + t % 3;
+        mbar_arrive_expect_tx(fb, 2 * bytes);
+        bulk_g2s(dst, src + (size_t)pa * bytes, bytes, fb);
+        bulk_g2s(dst + G * H * 2, src + (size_t)pb * bytes, bytes, fb);
       }
-      cp_async_commit();
     };
     constexpr uint32_t IDESC1 = idesc_bf16(H, true);
     const uint32_t a1_base = smem_u32(s_a1), ab_base = smem_u32(s_ab), w1r_base = smem_u32(s_w1r);
     const int4 zero4 = make_int4(0, 0, 0, 0);
-    load_ab(0, nt > 0 ? __ldg(tiles) : zero4);
-    load_ab(1, nt > 1 ? __ldg(tiles + 1) : zero4);
+    int4 td_cur = nt > 0 ? __ldg(tiles) : zero4, td_n1 = nt > 1 ? __ldg(tiles + 1) : zero4;
+    load_ab(0, td_cur);
+    load_ab(1, td_n1);
     int4 td_nx = nt > 2 ? __ldg(tiles + 2) : zero4;   // descriptor of tile t + 2, loaded one iteration early
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
       const int4 td_ld = td_nx;
       if (t + 3 < nt) td_nx = __ldg(tiles + t + 3);
       mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
+      SMB_TRACE(7, t, lane == 0);
       if (t >= 3) mbar_wait(bar + B_E2_DONE + t % 3, (t / 3 - 1) & 1);   // tile t - 3 left D[t % 3]
-      cp_async_wait<1>();
-      fence_async_smem();
-      __syncwarp();
+      mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
+      SMB_TRACE(1, t, lane == 0);
       if (lane == 0) {
         const uint32_t d = tmem + (uint32_t)(t % 3) * 128u;
         const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
         const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
-        const uint32_t b1[3] = {w1r_base, ab, ab + G * H * 2};
+        const uint32_t sbo_ab = (uint32_t)(td_cur.z & 0xff) * 16u;   // n * 16: column-group stride of the projection tiles
+        mma_ss(d, smem_desc(a1, 128, A1_SBO), smem_desc(w1r_base, 128, 512), IDESC1, 0);
+        mma_ss(d, smem_desc(a1 + 256, 128, A1_SBO), smem_desc(w1r_base + 256, 128, 512), IDESC1, 1);
 #pragma unroll
-        for (int ks = 0; ks < K1 / 16; ++ks)
-          mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(b1[ks >> 1] + (ks & 1) * 256, 128, 512), IDESC1, ks > 0);
+        for (int ks = 2; ks < K1 / 16; ++ks)
+          mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(ab + (ks >> 2) * (G * H * 2) + (ks & 1) * 256, 128, sbo_ab), IDESC1, 1);
+        SMB_TRACE(8, t, true);
         mma_commit(bar + B_A1_FREE + (t & 1));
         mma_commit(bar + B_D1_FULL + t % 3);
+        SMB_TRACE(9, t, true);
       }
       __syncwarp();
       // projection slot (t + 2) % 3 was read by GEMM1(t - 1)
       if (t >= 1) mbar_wait(bar + B_A1_FREE + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+      SMB_TRACE(10, t, lane == 0);
       load_ab(t + 2, td_ld);
+      SMB_TRACE(11, t, lane == 0);
+      td_cur = td_n1; td_n1 = td_ld;
     }
-    cp_async_wait<0>();
   } else {
     // =====================================================================================
     // GEMM2 issuer
@@ -662,6 +675,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const int zb = u & 1;
       mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
       fence_after_sync();
+      SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {
         const uint32_t d = tmem + (uint32_t)(u % 3) * 128u;
         if (ROLE == ROLE_V) {
@@ -748,7 +762,10 @@ int sms() {
 }
 
 template <int ROLE>
-int launch_ws(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
+int launch_ws(const EdgeArgs& a_in, int* bn_rows_out, cudaStream_t st) {
+  static const int dbg = getenv("SMB_WS_DBG") ? atoi(getenv("SMB_WS_DBG")) : 0;
+  EdgeArgs a = a_in;
+  a.dbg = dbg;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(edge_ws_kernel<ROLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<ROLE>::total);
@@ -763,6 +780,10 @@ int launch_ws(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
 }
 
 }  // namespace
+
+int debug_ws_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * TRACE_EVENTS * TRACE_TILES);
+}
 
 bool edge_ws_supported(const smb_model_dims& d, int n_max) {
   static const bool off = getenv("SMB_EDGE_TC5") != nullptr || getenv("SMB_EDGE_LEGACY") != nullptr;   // debugging aids

@@ -73,7 +73,10 @@ struct NodeArgs {
   const void* w2; const float* b2;
   const float* residual;   // optional [N][n2]
   float* out1;             // [N][n_pass]
-  uint32_t* out1_h;        // optional: the pass-through columns as packed bf16 pairs [N][n_pass/2] instead of out1
+  uint32_t* out1_h;        // optional: the pass-through columns as bf16, in the per-molecule operand layout of the
+                           // warp-specialised edge pipeline instead of out1: molecule block at byte a0 * 1024,
+                           // [part 0..3][column group of 8][atom][8 columns]  (needs mol_ptr)
+  const int* mol_ptr;
   float* out2;             // [N][n2_valid]
 };
 int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);
@@ -102,10 +105,11 @@ struct EdgeArgs {
   const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
   const void* w1r_u; const void* w2_u;   // tcgen05 operand images (EdgeMlpOff::w1r_u / w2_u)
   // warp-specialised pipeline (smb_edge_ws.cu)
-  const void* abh;         // [N][4H] bf16: the node projections as written by node_mlp_kernel (out1_h)
+  const void* abh;         // bf16 node projections in per-molecule operand layout (node_mlp_kernel out1_h)
   const int4* tiles;       // static tile list (build_tiles_kernel)
   const int* n_tiles;
   float* alpha_t;          // [tile][128 rows][16 heads]  (ROLE_K out; ROLE_V / ROLE_XV in)
+  int dbg;                 // SMB_WS_DBG bit mask (timing experiments only: results are wrong when set)
 };
 // bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
@@ -117,6 +121,7 @@ int launch_edge_tc5(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t 
 bool edge_ws_supported(const smb_model_dims& d, int n_max);
 int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st);
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
+int debug_ws_trace(long long* host_out);   // [8 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
 
 int launch_prep(const PrepArgs& a, cudaStream_t st);
 int launch_knn(const float* x, const int* mol_ptr, int n_mols, int k, int* nbr, int* deg, cudaStream_t st);

@@ -109,6 +109,13 @@ __global__ void __launch_bounds__(256, 1) node_mlp_kernel(NodeArgs a) {
     }
   };
 
+  // molecule of each row (only for the operand-image output)
+  int ma0 = 0, mn0 = 1, ma1 = 0, mn1 = 1;
+  if (MODE == 0 && a.out1_h) {
+    if (ok0) { const int m = a.atom_mol[row0]; ma0 = a.mol_ptr[m]; mn0 = a.mol_ptr[m + 1] - ma0; }
+    if (ok1) { const int m = a.atom_mol[row1]; ma1 = a.mol_ptr[m]; mn1 = a.mol_ptr[m + 1] - ma1; }
+  }
+
   float hid[2][NT_CHUNK][4];
 #pragma unroll
   for (int c = 0; c < 2; ++c)
@@ -157,9 +164,12 @@ __global__ void __launch_bounds__(256, 1) node_mlp_kernel(NodeArgs a) {
     for (int nt = 0; nt < NT_CHUNK; ++nt) {
       const int col = pc * 64 + nt * 8 + 2 * t;
       const float2 bb = *reinterpret_cast<const float2*>(a.b1 + col);
-      if (a.out1_h) {   // bf16 pairs for the tcgen05 edge pipeline (which rounds these operands to bf16 anyway)
-        if (ok0) a.out1_h[((size_t)row0 * a.n_pass + col) >> 1] = pack_bf16x2(c[nt][0] + bb.x, c[nt][1] + bb.y);
-        if (ok1) a.out1_h[((size_t)row1 * a.n_pass + col) >> 1] = pack_bf16x2(c[nt][2] + bb.x, c[nt][3] + bb.y);
+      if (a.out1_h) {   // bf16, per-molecule MN-major operand image for the tcgen05 edge pipeline (one bulk copy per tile)
+        const int part = col >> 7, cc = col & 127;
+        if (ok0) a.out1_h[((size_t)ma0 * 1024 + (size_t)part * mn0 * 256 + (cc >> 3) * mn0 * 16 + (row0 - ma0) * 16 + (cc & 7) * 2) >> 2] =
+            pack_bf16x2(c[nt][0] + bb.x, c[nt][1] + bb.y);
+        if (ok1) a.out1_h[((size_t)ma1 * 1024 + (size_t)part * mn1 * 256 + (cc >> 3) * mn1 * 16 + (row1 - ma1) * 16 + (cc & 7) * 2) >> 2] =
+            pack_bf16x2(c[nt][2] + bb.x, c[nt][3] + bb.y);
       } else {
         if (ok0) *reinterpret_cast<float2*>(a.out1 + (size_t)row0 * a.n_pass + col) = make_float2(c[nt][0] + bb.x, c[nt][1] + bb.y);
         if (ok1) *reinterpret_cast<float2*>(a.out1 + (size_t)row1 * a.n_pass + col) = make_float2(c[nt][2] + bb.x, c[nt][3] + bb.y);

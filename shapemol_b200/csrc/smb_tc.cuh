@@ -80,10 +80,25 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
 }
+// A failed try_wait returns after a few cycles, so a bare retry loop re-issues twice per ~8 cycles and takes issue
+// slots from the working warps of its scheduler (measured: 35 % of all executed instructions): back off between tries.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+  asm volatile("{\n\t.reg .pred P1;\n\t"
                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-               "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+               "@P1 bra DONE_%=;\n\t"
+               "WAIT_%=:\n\t"
+               "nanosleep.u32 %2;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+               "@!P1 bra WAIT_%=;\n\t"
+               "DONE_%=:\n\t}\n" :: "r"(smem_u32(b)), "r"(parity), "r"(20u) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine); completion is signalled on the mbarrier as `bytes` of transaction count
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 // named barrier over `n` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
