@@ -25,6 +25,7 @@ static void fill_edge_weights(EdgeArgs& e, const void* blob, const EdgeMlpOff& o
   e.w1r = vptr(blob, o.w1r); e.b1 = fptr(blob, o.b1); e.ln_g = fptr(blob, o.ln_g); e.ln_b = fptr(blob, o.ln_b);
   e.w2 = vptr(blob, o.w2); e.b2 = fptr(blob, o.b2);
   e.w1r_u = vptr(blob, o.w1r_u); e.w2_u = vptr(blob, o.w2_u);
+  e.w1r_f = vptr(blob, o.w1r_f); e.w2_f = vptr(blob, o.w2_f); e.beta_f = fptr(blob, o.beta_f);
 }
 static void fill_node_weights(NodeArgs& n, const void* blob, const NodeMlpOff& o) {
   n.w1 = vptr(blob, o.w1); n.b1 = fptr(blob, o.b1); n.ln_g = fptr(blob, o.ln_g); n.ln_b = fptr(blob, o.ln_b);
@@ -134,8 +135,11 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
-      if (ws) { n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr; }
       fill_node_weights(n, blob, y.x2h_pre);
+      if (ws) {   // bf16 operand images and LayerNorm-folded projections for the warp-specialised edge pipeline
+        n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;
+        n.w1 = vptr(blob, y.x2h_pre.w1_f); n.b1 = fptr(blob, y.x2h_pre.b1_f);
+      }
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
     {
@@ -162,8 +166,11 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
-      if (ws) { n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr; }
       fill_node_weights(n, blob, y.h2x_pre);
+      if (ws) {   // bf16 operand images and LayerNorm-folded projections for the warp-specialised edge pipeline
+        n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;
+        n.w1 = vptr(blob, y.h2x_pre.w1_f); n.b1 = fptr(blob, y.h2x_pre.b1_f);
+      }
       SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
     }
     {

@@ -46,7 +46,8 @@ constexpr int LS = 17;                 // padded row stride of per-row head scra
 constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
 constexpr int P_WARPS = 2, GRP_WARPS = 8, WARPS = 20, THREADS = WARPS * 32;   // 20 warps -> 96 registers per thread
 constexpr int LN_WARP0 = P_WARPS, E2_WARP0 = LN_WARP0 + GRP_WARPS, MMA_WARP = E2_WARP0 + GRP_WARPS;
-constexpr int BAR_LN = 1, BAR_E2 = 2;   // named barriers (0 is __syncthreads)
+constexpr int BAR_LN = 1, BAR_E2 = 2;   // named barriers (0 is __syncthreads); E2 group g uses BAR_E2 + g
+constexpr int E2_GRP_THREADS = 128;
 constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
 constexpr int GRP_THREADS = GRP_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
@@ -68,20 +69,20 @@ struct Plan {
   static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float2[2 buffers][2 halves][128]
   static constexpr int o_z = o_stat + 4096;          // ROLE_V: z^T operand, 2 x 32768
   static constexpr int o_e2 = o_z + (ROLE == ROLE_V ? 2 * TM * H * 2 : 0);
-  // E2 scratch: two staging slots (ROLE_K: q float[16][128]; ROLE_V: alpha float[128][16]; ROLE_XV: alpha | shape float[96])
+  // E2 scratch, one per group: two staging slots (ROLE_K: q float[16][128]; ROLE_V: alpha float[128][16];
+  // ROLE_XV: alpha | shape float[96]), then role scratch
   static constexpr int stage_bytes = ROLE == ROLE_XV ? 8192 + 384 : 8192;
+  static constexpr int n_slots = ROLE == ROLE_V ? 1 : 2;   // ROLE_V (z^T operands in smem) has room for one
   static constexpr int e_stage = 0;
-  static constexpr int e_log = 2 * stage_bytes;       // ROLE_K logits / ROLE_XV w : float[128][17]
+  static constexpr int e_log = n_slots * stage_bytes;       // ROLE_K logits / ROLE_XV w : float[128][17]
   static constexpr int e_red = e_log + 8704;          // ROLE_K float2[16][16]
-  static constexpr int e_ew = e_red + 2048;           // ROLE_K float[128]
-  static constexpr int e_part = 2 * stage_bytes;      // ROLE_V float2[128]
   static constexpr int e_rel = e_log + 8704;          // ROLE_XV float4[128]
   static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[16][16][4]
-  static constexpr int e2_bytes = ROLE == ROLE_K ? e_ew + 512 : ROLE == ROLE_V ? e_part + 1024 : e_o + 4096;
-  static constexpr int o_vnw = o_e2 + e2_bytes;       // ROLE_XV: vn_feat | vn_dir
+  static constexpr int e2_bytes = ROLE == ROLE_K ? e_red + 2048 : ROLE == ROLE_V ? n_slots * stage_bytes : e_o + 4096;
+  static constexpr int o_vnw = o_e2 + 2 * e2_bytes;       // ROLE_XV: vn_feat | vn_dir
   static constexpr int total = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);
   static_assert(total <= 227 * 1024, "shared memory budget");
-  static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0, "alignment");
+  static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0 && e2_bytes % 16 == 0, "alignment");
 };
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -128,15 +129,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
   // ---- once per CTA: weights -> smem, rings zeroed, TMEM allocation, mbarriers ----
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.w1r_u);
+    const uint4* src = reinterpret_cast<const uint4*>(a.w1r_f);
     uint4* dst = reinterpret_cast<uint4*>(s_w1r);
     for (int p = tid; p < 8192 / 16; p += THREADS) dst[p] = src[p];
-    const uint4* s2 = reinterpret_cast<const uint4*>(a.w2_u);
+    const uint4* s2 = reinterpret_cast<const uint4*>(a.w2_f);
     uint4* d2 = reinterpret_cast<uint4*>(s_w2);
     for (int p = tid; p < P::w2_bytes / 16; p += THREADS) d2[p] = s2[p];
     if (tid < H) {
-      s_g[tid] = a.ln_g[tid];
-      s_be[tid] = a.ln_b[tid];
+      s_g[tid] = 0.f;
+      s_be[tid] = a.beta_f[tid];   // beta / |gamma| (LayerNorm folded into the weight images)
       s_b2[tid] = ROLE == ROLE_XV ? (tid < kHeads ? a.b2[tid] : 0.f) : a.b2[tid];
     }
     if (ROLE == ROLE_XV)
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     for (int b = 0; b < 3; ++b) {
       mbar_init(bar + B_D1_FULL + b, 1);
       mbar_init(bar + B_D2_FULL + b, 1);
-      mbar_init(bar + B_E2_DONE + b, GRP_THREADS);
+      mbar_init(bar + B_E2_DONE + b, E2_GRP_THREADS);
       mbar_init(bar + B_AB_FULL + b, 1);
     }
     mbar_init_fence();
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     const int half = gw >> 2, qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
-    float2* s_stat = reinterpret_cast<float2*>(smem + P::o_stat);
+    float* s_stat = reinterpret_cast<float*>(smem + P::o_stat);
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
       const int b3 = t % 3, zb = t & 1;
@@ -278,23 +279,20 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       tmem_ld32(lane_addr + b3 * 128 + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(lane_addr + b3 * 128 + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       wait_ld();
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      // LayerNorm with the affine part folded into the operands (smb_host.cu fold_ln): the accumulator is already
+      // centred over the 128 channels and carries sign(gamma), so  z = relu(v * rstd + beta / |gamma|)
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
       if (!(a.dbg & 2))
 #pragma unroll
       for (int e = 0; e < 64; e += 4) {
         const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
-        s0 += f0; s1 += f1; s2 += f2; s3 += f3;
         q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
       }
-      const float sum = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
-      float2* st = s_stat + zb * (2 * TM);          // double-buffered: a fast thread may already be one tile ahead
-      st[half * TM + r] = make_float2(sum, sq);
+      const float sq = (q0 + q1) + (q2 + q3);
+      float* st = s_stat + zb * (2 * TM);          // double-buffered: a fast thread may already be one tile ahead
+      st[half * TM + r] = sq;
       named_sync(BAR_LN, GRP_THREADS);
-      const float2 ot = st[(half ^ 1) * TM + r];
-      const float mean = (sum + ot.x) * (1.f / H);
-      const float var = fmaxf((sq + ot.y) * (1.f / H) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-      const float shift = -mean * rstd;
+      const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
       if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % 3, ((t - 2) / 3) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
@@ -305,12 +303,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const int c = hp * 32 + e;
-          const float4 gg = *reinterpret_cast<const float4*>(s_g + half * 64 + c);
           const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + c);
-          const float y0 = fmaf(fmaf(__uint_as_float(v[c]), rstd, shift), gg.x, bb.x);
-          const float y1 = fmaf(fmaf(__uint_as_float(v[c + 1]), rstd, shift), gg.y, bb.y);
-          const float y2 = fmaf(fmaf(__uint_as_float(v[c + 2]), rstd, shift), gg.z, bb.z);
-          const float y3 = fmaf(fmaf(__uint_as_float(v[c + 3]), rstd, shift), gg.w, bb.w);
+          const float y0 = fmaf(__uint_as_float(v[c]), rstd, bb.x);
+          const float y1 = fmaf(__uint_as_float(v[c + 1]), rstd, bb.y);
+          const float y2 = fmaf(__uint_as_float(v[c + 2]), rstd, bb.z);
+          const float y3 = fmaf(__uint_as_float(v[c + 3]), rstd, bb.w);
           zp[e / 2] = pack_bf16_relu(y0, y1);
           zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
         }
@@ -332,44 +329,45 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     }
   } else if (warp < MMA_WARP) {
     // =====================================================================================
-    // E2: role epilogue on GEMM2's accumulator.  thread = (row, column half); every tile.
+    // E2: role epilogue on GEMM2's accumulator.  Two groups of four warps, thread = row (all 128 columns);
+    // group g owns tiles g, g + 2, ... so that two tiles' epilogues (and their barriers) overlap.
     // =====================================================================================
-    const int gw = warp - E2_WARP0;
-    const int half = gw >> 2, qd = warp & 3;
+    const int e2w = warp - E2_WARP0;
+    const int g = e2w >> 2, qd = warp & 3;
     const int r = qd * 32 + lane;            // TMEM lane = tile row (ROLE_V: output channel)
-    const int tg = gw * 32 + lane;           // thread index inside the role
+    const int tg = (e2w & 3) * 32 + lane;    // thread index inside the group
+    const int bar_id = BAR_E2 + g;
     const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
-    unsigned char* es = smem + P::o_e2;
+    unsigned char* es = smem + P::o_e2 + g * P::e2_bytes;
     float* s_log = reinterpret_cast<float*>(es + P::e_log);             // ROLE_K logits, ROLE_XV w
     float2* s_red = reinterpret_cast<float2*>(es + P::e_red);           // ROLE_K
-    float* s_ew = reinterpret_cast<float*>(es + P::e_ew);               // ROLE_K
-    float2* s_part = reinterpret_cast<float2*>(es + P::e_part);         // ROLE_V
     float4* s_rel = reinterpret_cast<float4*>(es + P::e_rel);           // ROLE_XV
     float* s_o = reinterpret_cast<float*>(es + P::e_o);                 // ROLE_XV
     float bn_s = 0.f, bn_q = 0.f;   // ROLE_XV: per-warp BatchNorm partial sums (lane & 15 = channel, lanes < 16)
 
-    // what tile `t` needs from global memory, staged one tile ahead: q rows / alpha tile / shape (cp.async,
-    // slot t & 1) and this thread's gate value / relative position (registers)
+    // what tile `t` needs from global memory, staged one tile (of this group) ahead: q rows / alpha tile / shape
+    // (cp.async, slot (t >> 1) & 1) and this thread's gate value / relative position (registers)
     float pre_ew = 0.f, pre_x = 0.f, pre_y = 0.f, pre_z = 0.f;
     auto stage = [&](int t, const Tile& T) {
-      unsigned char* slot = es + P::e_stage + (t & 1) * P::stage_bytes;
+      unsigned char* slot = es + P::e_stage + (P::n_slots == 2 ? (t >> 1) & 1 : 0) * P::stage_bytes;
       const int dl = min(T.dst_of(r), NDMAX - 1), sl = r - dl * T.deg;
       const bool valid = r < T.rows();
       if (ROLE == ROLE_K) {
         const float* src = a.q + (size_t)(T.a0 + T.d0) * H;
         float* dst = reinterpret_cast<float*>(slot);
-        for (int p = tg; p < T.nd * (H / 4); p += GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        for (int p = tg; p < T.nd * (H / 4); p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
         pre_ew = 0.f;
-        if (half == 0 && valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
+        if (valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
       } else {
         const float* src = a.alpha_t + (size_t)(t_begin + t) * (TM * kHeads);
         float* dst = reinterpret_cast<float*>(slot);
-        for (int p = tg; p < TM * kHeads / 4; p += GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+#pragma unroll
+        for (int p = tg; p < TM * kHeads / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
       }
       if (ROLE == ROLE_XV) {
         if (tg < kShape * 3 / 4) cp_async16(slot + TM * kHeads * 4 + tg * 16, a.shape + (size_t)T.mol * kShape * 3 + tg * 4);
         pre_x = pre_y = pre_z = 0.f;
-        if (half == 0 && valid) {
+        if (valid) {
           const int i = T.d0 + dl;
           const int j = __ldg(a.nbr + (size_t)(T.a0 + i) * KSTR + sl);
           const float* xi = a.x + (size_t)(T.a0 + i) * 3;
@@ -379,49 +377,51 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       }
     };
 
-    int4 td_cur = nt > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
-    int4 td_nx = nt > 1 ? __ldg(tiles + 1) : make_int4(0, 0, 0, 0);
-    if (nt > 0) stage(0, Tile(td_cur));
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 td_cur = g < nt ? __ldg(tiles + g) : zero4;
+    int4 td_nx = g + 2 < nt ? __ldg(tiles + g + 2) : zero4;
+    if (g < nt) stage(g, Tile(td_cur));
     cp_async_commit();
 #pragma unroll 1
-    for (int t = 0; t < nt; ++t) {
+    for (int t = g; t < nt; t += 2) {
       const Tile T(td_cur);
       const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
       td_cur = td_nx;
-      if (t + 2 < nt) td_nx = __ldg(tiles + t + 2);
-      if (t + 1 < nt) stage(t + 1, Tile(td_cur));   // slot (t + 1) & 1: its readers (tile t - 1) are behind the trailing barrier
-      cp_async_commit();
+      if (t + 4 < nt) td_nx = __ldg(tiles + t + 4);
+      if (P::n_slots == 2) {
+        if (t + 2 < nt) stage(t + 2, Tile(td_cur));   // the other slot: its readers (tile t - 2) are behind the trailing barrier
+        cp_async_commit();
+      }
       const int b3 = t % 3;
       const uint32_t dcol = (uint32_t)b3 * 128u;
       const int rows = T.rows();
       const bool valid = r < rows;
       const int dl = min(T.dst_of(r), NDMAX - 1);
-      const unsigned char* slot = es + P::e_stage + (t & 1) * P::stage_bytes;
+      const unsigned char* slot = es + P::e_stage + (P::n_slots == 2 ? (t >> 1) & 1 : 0) * P::stage_bytes;
       const float* s_q = reinterpret_cast<const float*>(slot);            // ROLE_K
       const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV
       const float* s_shape = reinterpret_cast<const float*>(slot + TM * kHeads * 4);   // ROLE_XV
 
-      cp_async_wait<1>();                      // this thread's share of tile t's staged data has landed
-      if (ROLE == ROLE_XV && half == 0) s_rel[r] = make_float4(relx, rely, relz, 0.f);
-      if (ROLE == ROLE_K && half == 0) s_ew[r] = ew_r;
+      if (P::n_slots == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
+      if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
       mbar_wait(bar + B_D2_FULL + b3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
-      named_sync(BAR_E2, GRP_THREADS);         // staged q / alpha / shape / rel / ew visible to the role
-      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); named_sync(BAR_E2, GRP_THREADS); continue; }
+      named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
+      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); named_sync(bar_id, E2_GRP_THREADS); continue; }
 
       if (ROLE == ROLE_K) {
-        float l[8];
-        {
+        float l[16];
+        // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
+        const float scale = 0.35355339059327373f * 1.4426950408889634f;   // 1/sqrt(dh) (dh = 8) x log2(e): softmax in base 2
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
           uint32_t v[64];
-          tmem_ld32(lane_addr + dcol + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld32(lane_addr + dcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld32(lane_addr + dcol + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32(lane_addr + dcol + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           wait_ld();
-          fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + b3);
-          // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
-          const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + half * 64);
-          const float scale = 0.35355339059327373f * 1.4426950408889634f;   // 1/sqrt(dh) (dh = 8) x log2(e): softmax in base 2
+          if (hf == 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); }
+          const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + hf * 64);
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const float4 qa = qrow[2 * hh], qb = qrow[2 * hh + 1];
@@ -433,64 +433,59 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
             acc = fmaf(__uint_as_float(v[8 * hh + 5]), qb.y, acc);
             acc = fmaf(__uint_as_float(v[8 * hh + 6]), qb.z, acc);
             acc = fmaf(__uint_as_float(v[8 * hh + 7]), qb.w, acc);
-            l[hh] = acc * scale;
-            s_log[r * LS + half * 8 + hh] = l[hh];
+            l[hf * 8 + hh] = acc * scale;
+            s_log[r * LS + hf * 8 + hh] = l[hf * 8 + hh];
           }
         }
-        named_sync(BAR_E2, GRP_THREADS);
-        // per (destination, head): max and 1 / sum exp2 over the destination's rows; 4 threads share a pair,
-        // each holds <= 8 of the <= 32 rows in registers
+        named_sync(bar_id, E2_GRP_THREADS);
+        // per (destination, head): max and 1 / sum exp2 over the destination's rows; 2 threads share a pair,
+        // each holds <= 16 of the <= 31 rows in registers
         {
-          const int part = tg & 3;
-          for (int pair = tg >> 2; pair < T.nd * kHeads; pair += GRP_THREADS / 4) {
+          const int part = tg & 1;
+          for (int pair = tg >> 1; pair < T.nd * kHeads; pair += E2_GRP_THREADS / 2) {
             const int pd = pair >> 4, hd = pair & 15;
             const float* col = s_log + (pd * T.deg) * LS + hd;
-            float lv[8];
+            float lv[16];
             float mx = -INFINITY;
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-              const int q = part + 4 * qq;
+            for (int qq = 0; qq < 16; ++qq) {
+              const int q = part + 2 * qq;
               lv[qq] = q < T.deg ? col[q * LS] : -INFINITY;
               mx = fmaxf(mx, lv[qq]);
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             float se = 0.f;
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) se += fast_ex2(lv[qq] - mx);
+            for (int qq = 0; qq < 16; ++qq) se += fast_ex2(lv[qq] - mx);
             se += __shfl_xor_sync(0xffffffffu, se, 1);
-            se += __shfl_xor_sync(0xffffffffu, se, 2);
             if (part == 0) s_red[pair] = make_float2(mx, 1.f / se);
           }
         }
-        named_sync(BAR_E2, GRP_THREADS);
+        named_sync(bar_id, E2_GRP_THREADS);
         {
-          const float ew = s_ew[r];
-          float o[8];
+          float o[16];
 #pragma unroll
-          for (int hh = 0; hh < 8; ++hh) {
-            const float2 mi = s_red[dl * kHeads + half * 8 + hh];
-            o[hh] = fast_ex2(l[hh] - mi.x) * (mi.y * ew);
+          for (int hh = 0; hh < 16; ++hh) {
+            const float2 mi = s_red[dl * kHeads + hh];
+            o[hh] = fast_ex2(l[hh] - mi.x) * (mi.y * ew_r);
           }
           if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.alpha_t + ((size_t)(t_begin + t) * TM + r) * kHeads + half * 8);
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            float4* dst = reinterpret_cast<float4*>(a.alpha_t + ((size_t)(t_begin + t) * TM + r) * kHeads);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
           }
         }
       } else if (ROLE == ROLE_V) {
-        // thread = output channel c (TMEM lane), columns = edge rows; this half covers rows [64 half, 64 half + 64)
+        // thread = output channel c (TMEM lane), columns = edge rows
         const int c = r, hq = c >> 3;
         const float b2c = s_b2[c];
         if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
-          if (half == 0) a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
-          fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + b3);
+          a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
         } else {
-          // this half owns the destinations pd = half, half + 2, ...: their deg <= 31 columns are read in
-          // power-of-two pieces, so the sum over a destination's rows is a branch-free in-thread loop
+          // a destination's deg <= 31 columns are read in power-of-two pieces, so the sum over its rows is a
+          // branch-free in-thread loop
           const float* al0 = s_al + hq;
-          for (int pd = half; pd < T.nd; pd += 2) {
+          for (int pd = 0; pd < T.nd; ++pd) {
             const int col = pd * T.deg;
             const uint32_t ta = lane_addr + dcol + col;
             uint32_t v16[16], v8[8], v4[4], v2[2], v1[1];
@@ -526,14 +521,16 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
             if (T.deg & 1) { const float w = al[0]; acc = fmaf(w, __uint_as_float(v1[0]), acc); asum += w; }
             a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, asum, acc);
           }
-          fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + b3);
         }
+        fence_before_sync();
+        mbar_arrive(bar + B_E2_DONE + b3);
       } else {   // ROLE_XV
-        if (half == 0) {
+        {
           uint32_t v[16];
           tmem_ld16(lane_addr + dcol, v);
           wait_ld();
+          fence_before_sync();
+          mbar_arrive(bar + B_E2_DONE + b3);
           if (valid) {
             const float4* al = reinterpret_cast<const float4*>(s_al + r * kHeads);
 #pragma unroll
@@ -546,11 +543,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
             }
           }
         }
-        fence_before_sync();
-        mbar_arrive(bar + B_E2_DONE + b3);
-        named_sync(BAR_E2, GRP_THREADS);
+        named_sync(bar_id, E2_GRP_THREADS);
         // o_i^a = sum_j alpha e_w w (x_i - x_j)
-        for (int p = tg; p < T.nd * kHeads; p += GRP_THREADS) {
+        for (int p = tg; p < T.nd * kHeads; p += E2_GRP_THREADS) {
           const int pd = p >> 4, hd = p & 15;
           const int r0 = pd * T.deg;
           float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -563,9 +558,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           float* o = s_o + (pd * kHeads + hd) * 4;
           o[0] = ox; o[1] = oy; o[2] = oz;
         }
-        named_sync(BAR_E2, GRP_THREADS);
+        named_sync(bar_id, E2_GRP_THREADS);
         // VN linear maps (shape_vn_layers.py:100,105): lanes 0..15 map_to_feat channel, 16..31 map_to_dir channel
-        for (int pd = gw; pd < T.nd; pd += GRP_WARPS) {
+        for (int pd = e2w & 3; pd < T.nd; pd += 4) {
           const int ch = lane & 15, which = lane >> 4;
           const float* w = s_vnw + (which * kHeads + ch) * kVnStride;
           const float* so = s_o + pd * kHeads * 4;
@@ -597,11 +592,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
       }
       SMB_TRACE(6, t, tg == 0);
-      named_sync(BAR_E2, GRP_THREADS);   // scratch and the staging slots are reused by the next tiles
+      named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slots are reused by the group's next tiles
+      if (P::n_slots == 1) {
+        if (t + 2 < nt) stage(t + 2, Tile(td_cur));
+        cp_async_commit();
+      }
     }   // tiles
     cp_async_wait<0>();
     if (ROLE == ROLE_XV && lane < 16) {
-      float* part = a.bn_partial + (size_t)(blockIdx.x * GRP_WARPS + gw) * 32;
+      float* part = a.bn_partial + (size_t)(blockIdx.x * GRP_WARPS + e2w) * 32;
       part[lane] = bn_s;
       part[16 + lane] = bn_q;
     }

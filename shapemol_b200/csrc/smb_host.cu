@@ -49,9 +49,12 @@ EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
   e.b2 = c.take((gate ? 4 : n2) * 4);
   e.w1r_u = c.take((size_t)32 * H * 2);
   e.w2_u = gate ? e.w1r_u : c.take((size_t)n2 * H * 2);
+  e.w1r_f = gate ? e.w1r_u : c.take((size_t)32 * H * 2);
+  e.w2_f = gate ? e.w1r_u : c.take((size_t)n2 * H * 2);
+  e.beta_f = gate ? e.ln_b : c.take(H * 4);
   return e;
 }
-NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2) {
+NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2, bool folded = false) {
   const int H = d.hidden;
   const size_t fb = frag_bytes(d);
   NodeMlpOff n;
@@ -61,6 +64,8 @@ NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2
   n.ln_b = c.take(H * 4);
   n.w2 = c.take((size_t)(n2 / 8) * (H / 16) * 32 * fb);
   n.b2 = c.take(n2 * 4);
+  n.w1_f = folded ? c.take((size_t)(n1 / 8) * (k1 / 16) * 32 * fb) : n.w1;
+  n.b1_f = folded ? c.take(n1 * 4) : n.b1;
   return n;
 }
 }  // namespace
@@ -91,9 +96,9 @@ ModelLayout build_layout(const smb_model_dims& d) {
     y.hv = carve_edge(c, d, H, false);
     y.xk = carve_edge(c, d, H, false);
     y.xv = carve_edge(c, d, kHeads, false);
-    y.x2h_pre = carve_node(c, d, 5 * H, H + kShape, H);
+    y.x2h_pre = carve_node(c, d, 5 * H, H + kShape, H, true);
     y.node_out = carve_node(c, d, H, 2 * H, H);
-    y.h2x_pre = carve_node(c, d, 5 * H, H + kShape, H);
+    y.h2x_pre = carve_node(c, d, 5 * H, H + kShape, H, true);
     y.vn_feat = c.take(kHeads * kVnStride * 4);
     y.vn_dir = c.take(kHeads * kVnStride * 4);
   }
@@ -227,6 +232,33 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
     put(blob, L.inv_g, get(p + "1.weight"), kShape); put(blob, L.inv_bb, get(p + "1.bias"), kShape);
     put(blob, L.inv_w2, get(p + "3.weight"), kShape * kShape); put(blob, L.inv_b2, get(p + "3.bias"), kShape);
   }
+  // LayerNorm folding (warp-specialised edge pipeline).  For an edge MLP with first Linear W1 / b1 and LayerNorm
+  // (gamma, beta):  LN(v)_c = gamma_c (v_c - mean) rstd + beta_c.  Exact algebra:
+  //   * subtracting the mean over the hidden channels from every column of W1 (and from b1) makes mean = 0;
+  //   * relu(gamma_c n_c + beta_c) = |gamma_c| relu(sign(gamma_c) n_c + beta_c / |gamma_c|): the sign goes into
+  //     channel c of the first Linear (the variance does not see it), |gamma_c| into column c of the second Linear.
+  // fold.f[c] = sign, fold.mag[c] = |gamma_c| (floored so that gamma = 0 stays finite), fold.beta[c] = beta_c / |gamma_c|.
+  struct Fold { std::vector<float> f, mag, beta; };
+  auto make_fold = [&](const std::string& p) {
+    const float* g = get(p + ".net.1.weight");
+    const float* b = get(p + ".net.1.bias");
+    Fold fo;
+    fo.f.resize(H); fo.mag.resize(H); fo.beta.resize(H);
+    for (int c = 0; c < H; ++c) {
+      fo.f[c] = g[c] < 0.f ? -1.f : 1.f;
+      fo.mag[c] = fmaxf(fabsf(g[c]), 1e-20f);
+      fo.beta[c] = b[c] / fo.mag[c];
+    }
+    return fo;
+  };
+  // column k of a [H x ld] row-major weight, centred over the H rows and sign-folded
+  auto folded_col = [&](const float* w, int ld, int k, const Fold& fo, std::vector<float>& out) {
+    double m = 0.0;
+    for (int n = 0; n < H; ++n) m += w[(size_t)n * ld + k];
+    m /= H;
+    out.resize(H);
+    for (int n = 0; n < H; ++n) out[n] = fo.f[n] * (float)((double)w[(size_t)n * ld + k] - m);
+  };
   auto pack_edge = [&](const EdgeMlpOff& e, const std::string& p, int n2, int ld1, bool gate) {
     const float* w1 = get(p + ".net.0.weight");
     pack_frags(blob + e.w1r, H / 8, 2, prec, [&](int n, int k) { return k < kRbf ? w1[(size_t)n * ld1 + k] : 0.f; });
@@ -247,6 +279,18 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
       for (int n = 0; n < n2; ++n)
         for (int k = 0; k < H; ++k)
           u2[((size_t)(n / 8) * 2048 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2[(size_t)n * H + k]);
+      const Fold fo = make_fold(p);
+      uint16_t* f1 = reinterpret_cast<uint16_t*>(blob + e.w1r_f);
+      std::vector<float> col;
+      for (int k = 0; k < kRbf; ++k) {
+        folded_col(w1, ld1, k, fo, col);
+        for (int n = 0; n < H; ++n) f1[((size_t)(n / 8) * 512 + (size_t)k * 16 + (n % 8) * 2) / 2] = f2bf(col[n]);
+      }
+      uint16_t* f2 = reinterpret_cast<uint16_t*>(blob + e.w2_f);
+      for (int n = 0; n < n2; ++n)
+        for (int k = 0; k < H; ++k)
+          f2[((size_t)(n / 8) * 2048 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2[(size_t)n * H + k] * fo.mag[k]);
+      put(blob, e.beta_f, fo.beta.data(), H);
     }
   };
   pack_edge(L.gate, "refine_net.edge_pred_layer", 0, kRbf, true);
@@ -282,6 +326,30 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
       pack_frags(blob + n.w1, 5 * H / 8, (H + kShape) / 16, prec, W);
       float* b1 = reinterpret_cast<float*>(blob + n.b1);
       for (int r = 0; r < H; ++r) { b1[r] = bk[r]; b1[2 * H + r] = bv[r]; b1[4 * H + r] = bq[r]; }
+      {  // LayerNorm-folded pass-through blocks (A_k | B_k | A_v | B_v); the query block is unchanged
+        const Fold fk = make_fold(kf), fv = make_fold(vf);
+        const int K1 = H + kShape;
+        std::vector<float> wf((size_t)5 * H * K1);
+        for (int blk = 0; blk < 5; ++blk)
+          for (int k = 0; k < K1; ++k) {
+            if (blk == 4) { for (int r = 0; r < H; ++r) wf[(size_t)(blk * H + r) * K1 + k] = W(blk * H + r, k); continue; }
+            const Fold& fo = blk < 2 ? fk : fv;
+            double m = 0.0;
+            for (int r = 0; r < H; ++r) m += W(blk * H + r, k);
+            m /= H;
+            for (int r = 0; r < H; ++r) wf[(size_t)(blk * H + r) * K1 + k] = fo.f[r] * (float)((double)W(blk * H + r, k) - m);
+          }
+        pack_frags(blob + n.w1_f, 5 * H / 8, K1 / 16, prec, [&](int n_, int k) { return wf[(size_t)n_ * K1 + k]; });
+        float* bf = reinterpret_cast<float*>(blob + n.b1_f);
+        double mk = 0.0, mv = 0.0;
+        for (int r = 0; r < H; ++r) { mk += bk[r]; mv += bv[r]; }
+        mk /= H; mv /= H;
+        for (int r = 0; r < H; ++r) {
+          bf[r] = fk.f[r] * (float)((double)bk[r] - mk); bf[H + r] = 0.f;
+          bf[2 * H + r] = fv.f[r] * (float)((double)bv[r] - mv); bf[3 * H + r] = 0.f;
+          bf[4 * H + r] = bq[r];
+        }
+      }
       put(blob, n.ln_g, get(qf + ".net.1.weight"), H);
       put(blob, n.ln_b, get(qf + ".net.1.bias"), H);
       const float* w2 = get(qf + ".net.3.weight");

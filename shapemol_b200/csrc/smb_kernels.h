@@ -104,6 +104,7 @@ struct EdgeArgs {
   // weights
   const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
   const void* w1r_u; const void* w2_u;   // tcgen05 operand images (EdgeMlpOff::w1r_u / w2_u)
+  const void* w1r_f; const void* w2_f; const float* beta_f;   // LayerNorm-folded images (EdgeMlpOff::w1r_f / w2_f / beta_f)
   // warp-specialised pipeline (smb_edge_ws.cu)
   const void* abh;         // bf16 node projections in per-molecule operand layout (node_mlp_kernel out1_h)
   const int4* tiles;       // static tile list (build_tiles_kernel)

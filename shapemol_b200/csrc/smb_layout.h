@@ -29,6 +29,12 @@ struct EdgeMlpOff {
   // tcgen05 (UMMA) operand images, bf16, no swizzle (smb_tc.cuh): used by the plain-bf16 edge kernels
   size_t w1r_u;  // [32 k][H n] MN-major: byte(k, n) = (n/8)*512 + k*16 + (n%8)*2      (k >= 20 zero)
   size_t w2_u;   // [N2 n][H k] K-major:  byte(n, k) = (n/8)*2048 + (k/8)*128 + (n%8)*16 + (k%8)*2
+  // LayerNorm-folded images for the warp-specialised pipeline (smb_edge_ws.cu; see fold_ln in smb_host.cu):
+  // first-Linear columns centred over the 128 hidden channels and multiplied by sign(gamma), second-Linear
+  // k-columns multiplied by |gamma|, so that the kernel's LayerNorm is  z = relu(v * rstd + beta / |gamma|)
+  size_t w1r_f;  // as w1r_u
+  size_t w2_f;   // as w2_u
+  size_t beta_f; // [H] fp32
 };
 
 // Node-level chain: Y1 = X W1^T + b1 ; first n_pass columns are written out as they are, the last H
@@ -40,6 +46,9 @@ struct NodeMlpOff {
   size_t ln_b;   // [H]
   size_t w2;     // B fragments [N2/8][H/16][32]
   size_t b2;     // [N2]
+  // x2h_pre / h2x_pre only: W1 / b1 with the four pass-through blocks LayerNorm-folded like EdgeMlpOff::w1r_f
+  size_t w1_f;
+  size_t b1_f;
 };
 
 struct LayerOff {

@@ -34,7 +34,6 @@ def main():
     torch.cuda.synchronize()
     lib = _lib.load()
     buf = np.zeros((12, 128), dtype=np.int64)
-    lib.smb_debug_ws_trace.argtypes = [C.c_void_p]
     rc = lib.smb_debug_ws_trace(buf.ctypes.data)
     assert rc == 0, rc
     nt = int((buf[0] > 0).sum())
