@@ -30,6 +30,7 @@ static void fill_edge_weights(EdgeArgs& e, const void* blob, const EdgeMlpOff& o
 static void fill_node_weights(NodeArgs& n, const void* blob, const NodeMlpOff& o) {
   n.w1 = vptr(blob, o.w1); n.b1 = fptr(blob, o.b1); n.ln_g = fptr(blob, o.ln_g); n.ln_b = fptr(blob, o.ln_b);
   n.w2 = vptr(blob, o.w2); n.b2 = fptr(blob, o.b2);
+  n.w1_t = vptr(blob, o.w1_t); n.w2_t = vptr(blob, o.w2_t); n.beta_t = fptr(blob, o.beta_t);
 }
 
 #define SMB_LAUNCH(expr)                                                                     \
@@ -101,6 +102,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
 
   // warp-specialised tcgen05 pipeline for the three attention roles (plain-bf16 mode, <= 32 atoms per molecule)
   const bool ws = edge_ws_supported(d, n_max);
+  const bool node_tc5 = ws && node_tc5_supported(d, n_max);
   int4* tiles = wptr<int4>(ws_base, W.tiles + 16);
   int* n_tiles = wptr<int>(ws_base, W.tiles);
   if (ws) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
@@ -140,7 +142,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
         n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;
         n.w1 = vptr(blob, y.x2h_pre.w1_f); n.b1 = fptr(blob, y.x2h_pre.b1_f);
       }
-      SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_PRE, node_tc5 ? launch_node_pre_tc5(n, st) : launch_node_mlp(d, n, st));
     }
     {
       EdgeArgs e = eb;
@@ -171,7 +173,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
         n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;
         n.w1 = vptr(blob, y.h2x_pre.w1_f); n.b1 = fptr(blob, y.h2x_pre.b1_f);
       }
-      SMB_TIMED(SMB_PROF_NODE_PRE, launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_PRE, node_tc5 ? launch_node_pre_tc5(n, st) : launch_node_mlp(d, n, st));
     }
     {
       EdgeArgs e = eb;

@@ -66,6 +66,9 @@ NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2
   n.b2 = c.take(n2 * 4);
   n.w1_f = folded ? c.take((size_t)(n1 / 8) * (k1 / 16) * 32 * fb) : n.w1;
   n.b1_f = folded ? c.take(n1 * 4) : n.b1;
+  n.w1_t = folded ? c.take((size_t)5 * kNodeChunkBytes) : n.w1;
+  n.w2_t = folded ? c.take((size_t)H * H * 2) : n.w2;
+  n.beta_t = folded ? c.take(H * 4) : n.ln_b;
   return n;
 }
 }  // namespace
@@ -349,6 +352,40 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
           bf[2 * H + r] = fv.f[r] * (float)((double)bv[r] - mv); bf[3 * H + r] = 0.f;
           bf[4 * H + r] = bq[r];
         }
+        // tcgen05 images (node_pre_tc5_kernel): chunk 0 = the query MLP's hidden block, folded with its own LayerNorm
+        const Fold fq = make_fold(qf);
+        uint16_t* wt = reinterpret_cast<uint16_t*>(blob + n.w1_t);
+        auto put_t = [&](int chunk, int nn, int k, float v) {
+          wt[((size_t)chunk * kNodeChunkBytes + (size_t)(nn / 8) * (kNodeKx / 8) * 128 + (size_t)(k / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2) / 2] = f2bf(v);
+        };
+        auto put_bias = [&](int chunk, int nn, float b) {
+          const uint16_t hi = f2bf(b);
+          wt[((size_t)chunk * kNodeChunkBytes + (size_t)(nn / 8) * (kNodeKx / 8) * 128 + (size_t)(K1 / 8) * 128 + (nn % 8) * 16) / 2] = hi;
+          wt[((size_t)chunk * kNodeChunkBytes + (size_t)(nn / 8) * (kNodeKx / 8) * 128 + (size_t)(K1 / 8) * 128 + (nn % 8) * 16 + 2) / 2] = f2bf(b - bf2f(hi));
+        };
+        for (int blk = 0; blk < 4; ++blk)
+          for (int r = 0; r < H; ++r) {
+            for (int k = 0; k < K1; ++k) put_t(1 + blk, r, k, wf[(size_t)(blk * H + r) * K1 + k]);
+            put_bias(1 + blk, r, bf[blk * H + r]);
+          }
+        {
+          double mb = 0.0;
+          for (int r = 0; r < H; ++r) mb += bq[r];
+          mb /= H;
+          for (int k = 0; k < K1; ++k) {
+            double m = 0.0;
+            for (int r = 0; r < H; ++r) m += W(4 * H + r, k);
+            m /= H;
+            for (int r = 0; r < H; ++r) put_t(0, r, k, fq.f[r] * (float)((double)W(4 * H + r, k) - m));
+          }
+          for (int r = 0; r < H; ++r) put_bias(0, r, fq.f[r] * (float)((double)bq[r] - mb));
+        }
+        const float* w2q = get(qf + ".net.3.weight");
+        uint16_t* w2t = reinterpret_cast<uint16_t*>(blob + n.w2_t);
+        for (int nn = 0; nn < H; ++nn)
+          for (int k = 0; k < H; ++k)
+            w2t[((size_t)(nn / 8) * 2048 + (size_t)(k / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2q[(size_t)nn * H + k] * fq.mag[k]);
+        put(blob, n.beta_t, fq.beta.data(), H);
       }
       put(blob, n.ln_g, get(qf + ".net.1.weight"), H);
       put(blob, n.ln_b, get(qf + ".net.1.bias"), H);

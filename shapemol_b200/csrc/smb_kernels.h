@@ -78,8 +78,13 @@ struct NodeArgs {
                            // [part 0..3][column group of 8][atom][8 columns]  (needs mol_ptr)
   const int* mol_ptr;
   float* out2;             // [N][n2_valid]
+  const void *w1_t, *w2_t; const float* beta_t;   // tcgen05 operand images (NodeMlpOff::w1_t / w2_t / beta_t)
 };
 int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);
+// tcgen05 implementation of XMODE_H_INV for the warp-specialised edge pipeline (smb_node_tc5.cu): needs out1_h,
+// mol_ptr, w1_t, w2_t, beta_t, b2
+bool node_tc5_supported(const smb_model_dims& d, int n_max);
+int launch_node_pre_tc5(const NodeArgs& a, cudaStream_t st);
 
 // Edge kernels (smb_edge_attn.cu)
 enum EdgeRole { ROLE_GATE = 0, ROLE_K = 1, ROLE_V = 2, ROLE_XV = 3 };

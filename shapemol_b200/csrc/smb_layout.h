@@ -49,7 +49,16 @@ struct NodeMlpOff {
   // x2h_pre / h2x_pre only: W1 / b1 with the four pass-through blocks LayerNorm-folded like EdgeMlpOff::w1r_f
   size_t w1_f;
   size_t b1_f;
+  // x2h_pre / h2x_pre only: tcgen05 operand images for node_pre_tc5_kernel (smb_node_tc5.cu).  Every block is
+  // LayerNorm-folded (the four pass-through blocks with their edge MLP's LayerNorm, the hidden block with the query
+  // MLP's); the bias rides in two extra K columns (bf16 hi | lo) against constant-one activations.
+  size_t w1_t;   // 5 chunks [hidden | A_k | B_k | A_v | B_v] of [128 n][kNodeKx k] bf16, K-major:
+                 //   byte(n, k) = (n/8)*(kNodeKx/8)*128 + (k/8)*128 + (n%8)*16 + (k%8)*2
+  size_t w2_t;   // [128 n][128 k] K-major (as EdgeMlpOff::w2_u), k-columns multiplied by |gamma|
+  size_t beta_t; // [H] beta / |gamma|
 };
+constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
+constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
 
 struct LayerOff {
   EdgeMlpOff hk, hv, xk, xv;
