@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 # Linear(308->128) + Linear(128->128) + <q,k>
 F_REF_EDGE_K = 2 * (308 * 128 + 128 * 128) + 2 * 128
 F_MIN_EDGE_K = 2 * (20 * 128 + 128 * 128) + 2 * 128       # with the first Linear factored to node level
-KERNELS_PER_STEP = 4 + 8 * 9 + 1 + 1 + 1                   # prep, embed, knn, gate | 8 x (3 node, 4 edge, bn, apply) | head | posterior | t--
+KERNELS_PER_STEP = 5 + 8 * 9 + 1 + 1 + 1                   # prep, embed, knn, tile list, gate | 8 x (3 node, 4 edge, bn, apply) | head | posterior | t--
 
 
 def ref_like_config(k=32):
@@ -137,7 +137,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16x3', 'bf16'])
+    ap.add_argument('--no-parity-mode', action='store_true', help='skip the secondary bf16x3 (fp32-parity) measurement')
     ap.add_argument('--shapes', type=int, default=100)
     ap.add_argument('--per-shape', type=int, default=50)
     ap.add_argument('--k', type=int, default=32)
@@ -291,6 +292,28 @@ def main():
         else:
             roof = {'kernel': args.prof_kernel, 'ms_per_launch': kms, 'launches_per_step': n_launch, 'share_of_step': n_launch * kms / ms}
 
+    # ---- secondary: the fp32-parity arithmetic mode (split-bf16 products) on the same workload ----
+    parity_mode = None
+    if rank == 0 and world == 1 and args.precision == 'bf16' and not args.no_parity_mode:
+        m3 = build_model(args.k, 'bf16x3').to(dev).train()
+        s3 = Sampler(m3._engine(), pos.to(dev), v.to(dev), batch.to(dev), shape.to(dev), num_steps=1000, noise='philox', seed=2021,
+                     atom_offset=atom_offset, keep_traj=False, use_graph=True, n_mols=B)
+        s3._step_body(0)
+        s3._capture(1)
+        for _ in range(3):
+            s3.graph.replay()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            s3.graph.replay()
+        p1.record()
+        torch.cuda.synchronize()
+        ms3 = p0.elapsed_time(p1) / 5
+        parity_mode = {'dtype': 'bf16x3 (split-bf16 products, fp32 accumulate): x0 / logits within 1e-3 of the fp32 reference',
+                       'ms_per_step': ms3, 'mol_steps_per_s': B / (ms3 * 1e-3), 'steps': 5}
+        del s3, m3
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, threads, bc = cpu_reference_arm(args.k, args.cpu_mols, 3, 1)
@@ -305,7 +328,7 @@ def main():
             'metric': 'molecules/sec (1000-step sampling)', 'value': val, 'unit': 'molecules/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32-parity mode)'
-            if args.precision == 'bf16x3' else 'bf16 (fp32 accumulate)',
+            if args.precision == 'bf16x3' else 'bf16 (tcgen05 MLP contractions, fp32 accumulate; everything else fp32)',
             'data': 'synthetic',
             'config': {'workload': workload, 'molecules_per_gpu': B, 'atoms_per_gpu': N, 'edges_per_gpu': E,
                        'l2': 'per-step working set %.0f MB > 126 MB L2 (no flush needed)' % (N * 7.2e3 / 1e6),
@@ -316,7 +339,7 @@ def main():
             'e2e': {'value': total_mols / (1000.0 * e2e_ms * 1e-3), 'unit': 'molecules/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': hs.h2d_bytes, 'd2h_bytes_per_step': hs.d2h_bytes},
             'gpu_launches': KERNELS_PER_STEP * args.steps,
-            'roofline': roof, 'cpu_baseline': cpu, 'final_gather_ms': gather_ms,
+            'roofline': roof, 'cpu_baseline': cpu, 'fp32_parity_mode': parity_mode, 'final_gather_ms': gather_ms,
         }
         print(json.dumps(line))
     if world > 1:

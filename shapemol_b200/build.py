@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get('SMB_NVCC_EXTRA', '').split() + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

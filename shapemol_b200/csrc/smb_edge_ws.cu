@@ -54,12 +54,14 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t Z_COL = 384;
 
 // mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 9, B_E2_DONE = 12, B_AB_FULL = 15, N_BARS = 18 };
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 10, B_E2_DONE = 14, B_AB_FULL = 18, N_BARS = 21 };
+// accumulator ring: ROLE_V keeps z in shared memory, so all 512 TMEM columns hold accumulators
+template <int ROLE> struct Ring { static constexpr int ND = ROLE == ROLE_V ? 4 : 3; };
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 18 mbarriers
-  static constexpr int o_tmem = 144;
+  static constexpr int o_bar = 0;                 // 21 mbarriers
+  static constexpr int o_tmem = 192;
   static constexpr int o_vec = 256;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
@@ -108,6 +110,7 @@ __device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
 template <int ROLE>
 __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
   using P = Plan<ROLE>;
+  constexpr int ND = Ring<ROLE>::ND;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::o_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::o_tmem);
@@ -157,12 +160,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       mbar_init(bar + B_A1_FREE + b, 1);
       mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
     }
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(bar + B_D1_FULL + b, 1);
       mbar_init(bar + B_D2_FULL + b, 1);
       mbar_init(bar + B_E2_DONE + b, E2_GRP_THREADS);
-      mbar_init(bar + B_AB_FULL + b, 1);
     }
+    for (int b = 0; b < 3; ++b) mbar_init(bar + B_AB_FULL + b, 1);
     mbar_init_fence();
   }
   fence_async_smem();
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     float* s_stat = reinterpret_cast<float*>(smem + P::o_stat);
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
-      const int b3 = t % 3, zb = t & 1;
-      mbar_wait(bar + B_D1_FULL + b3, (t / 3) & 1);
+      const int b3 = t % ND, zb = t & 1;
+      mbar_wait(bar + B_D1_FULL + b3, (t / ND) & 1);
       fence_after_sync();
       SMB_TRACE(2, t, gw == 0 && lane == 0);
       uint32_t v[64];
@@ -281,36 +284,19 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       wait_ld();
       // LayerNorm with the affine part folded into the operands (smb_host.cu fold_ln): the accumulator is already
       // centred over the 128 channels and carries sign(gamma), so  z = relu(v * rstd + beta / |gamma|)
-      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-      if (!(a.dbg & 2))
-#pragma unroll
-      for (int e = 0; e < 64; e += 4) {
-        const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
-        q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
-      }
-      const float sq = (q0 + q1) + (q2 + q3);
+      const float sq = ln_sumsq64(v);
       float* st = s_stat + zb * (2 * TM);          // double-buffered: a fast thread may already be one tile ahead
       st[half * TM + r] = sq;
       named_sync(BAR_LN, GRP_THREADS);
       const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
-      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % 3, ((t - 2) / 3) & 1);
+      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % ND, ((t - 2) / ND) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
       if (!(a.dbg & 2))
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
         uint32_t zp[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const int c = hp * 32 + e;
-          const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + c);
-          const float y0 = fmaf(__uint_as_float(v[c]), rstd, bb.x);
-          const float y1 = fmaf(__uint_as_float(v[c + 1]), rstd, bb.y);
-          const float y2 = fmaf(__uint_as_float(v[c + 2]), rstd, bb.z);
-          const float y3 = fmaf(__uint_as_float(v[c + 3]), rstd, bb.w);
-          zp[e / 2] = pack_bf16_relu(y0, y1);
-          zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
-        }
+        ln_apply32(v, hp * 32, rstd, s_be + half * 64 + hp * 32, zp);
         if (ROLE == ROLE_V) {
           // z^T operand: K-major [row][k]; this thread owns k = 64 half .. 64 half + 63 of row r
           unsigned char* zrow = smem + P::o_z + zb * (TM * H * 2) + (r >> 3) * 2048 + (r & 7) * 16 + (half * 8 + hp * 4) * 128;
@@ -392,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (t + 2 < nt) stage(t + 2, Tile(td_cur));   // the other slot: its readers (tile t - 2) are behind the trailing barrier
         cp_async_commit();
       }
-      const int b3 = t % 3;
+      const int b3 = t % ND;
       const uint32_t dcol = (uint32_t)b3 * 128u;
       const int rows = T.rows();
       const bool valid = r < rows;
@@ -404,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
       if (P::n_slots == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
-      mbar_wait(bar + B_D2_FULL + b3, (t / 3) & 1);
+      mbar_wait(bar + B_D2_FULL + b3, (t / ND) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
       named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
@@ -425,14 +411,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const float4 qa = qrow[2 * hh], qb = qrow[2 * hh + 1];
-            float acc = __uint_as_float(v[8 * hh]) * qa.x;
-            acc = fmaf(__uint_as_float(v[8 * hh + 1]), qa.y, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 2]), qa.z, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 3]), qa.w, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 4]), qb.x, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 5]), qb.y, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 6]), qb.z, acc);
-            acc = fmaf(__uint_as_float(v[8 * hh + 7]), qb.w, acc);
+            uint64_t acc2 = mul2(pk2u(v[8 * hh], v[8 * hh + 1]), pk2(qa.x, qa.y));
+            acc2 = fma2(pk2u(v[8 * hh + 2], v[8 * hh + 3]), pk2(qa.z, qa.w), acc2);
+            acc2 = fma2(pk2u(v[8 * hh + 4], v[8 * hh + 5]), pk2(qb.x, qb.y), acc2);
+            acc2 = fma2(pk2u(v[8 * hh + 6], v[8 * hh + 7]), pk2(qb.z, qb.w), acc2);
+            const float acc = sum2(acc2);
             l[hf * 8 + hh] = acc * scale;
             s_log[r * LS + hf * 8 + hh] = l[hf * 8 + hh];
           }
@@ -636,12 +619,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (t + 3 < nt) td_nx = __ldg(tiles + t + 3);
       mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
       SMB_TRACE(7, t, lane == 0);
-      if (t >= 3) mbar_wait(bar + B_E2_DONE + t % 3, (t / 3 - 1) & 1);   // tile t - 3 left D[t % 3]
+      if (t >= ND) mbar_wait(bar + B_E2_DONE + t % ND, (t / ND - 1) & 1);   // tile t - ND left D[t % ND]
       mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(1, t, lane == 0);
       if (lane == 0) {
-        const uint32_t d = tmem + (uint32_t)(t % 3) * 128u;
+        const uint32_t d = tmem + (uint32_t)(t % ND) * 128u;
         const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
         const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
         const uint32_t sbo_ab = (uint32_t)(td_cur.z & 0xff) * 16u;   // n * 16: column-group stride of the projection tiles
@@ -652,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(ab + (ks >> 2) * (G * H * 2) + (ks & 1) * 256, 128, sbo_ab), IDESC1, 1);
         SMB_TRACE(8, t, true);
         mma_commit(bar + B_A1_FREE + (t & 1));
-        mma_commit(bar + B_D1_FULL + t % 3);
+        mma_commit(bar + B_D1_FULL + t % ND);
         SMB_TRACE(9, t, true);
       }
       __syncwarp();
@@ -676,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       fence_after_sync();
       SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {
-        const uint32_t d = tmem + (uint32_t)(u % 3) * 128u;
+        const uint32_t d = tmem + (uint32_t)(u % ND) * 128u;
         if (ROLE == ROLE_V) {
           const uint32_t zt = smem_u32(smem + P::o_z + zb * (TM * H * 2));
 #pragma unroll
@@ -687,7 +670,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           for (int ks = 0; ks < H / 16; ++ks)
             mma_ts(d, tmem + Z_COL + zb * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
         }
-        mma_commit(bar + B_D2_FULL + u % 3);
+        mma_commit(bar + B_D2_FULL + u % ND);
       }
       __syncwarp();
     }

@@ -229,13 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
         mbar_arrive(bar + B_D_FREE + db);
         if (s == 0) {
           // LayerNorm folded into the operands: the accumulator is centred and carries sign(gamma)
-          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-          for (int e = 0; e < 64; e += 4) {
-            const float f0 = __uint_as_float(v[e]), f1 = __uint_as_float(v[e + 1]), f2 = __uint_as_float(v[e + 2]), f3 = __uint_as_float(v[e + 3]);
-            q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1); q2 = fmaf(f2, f2, q2); q3 = fmaf(f3, f3, q3);
-          }
-          const float sq = (q0 + q1) + (q2 + q3);
+          const float sq = ln_sumsq64(v);
           float* st = s_stat + (it & 1) * (2 * TM);
           st[half * TM + r] = sq;
           named_sync(BAR_LN, E_THREADS);
@@ -243,13 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
             uint32_t zp[16];
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const int c = hp * 32 + e;
-              const float4 bb = *reinterpret_cast<const float4*>(s_beta + half * 64 + c);
-              zp[e / 2] = pack_bf16_relu(fmaf(__uint_as_float(v[c]), rstd, bb.x), fmaf(__uint_as_float(v[c + 1]), rstd, bb.y));
-              zp[e / 2 + 1] = pack_bf16_relu(fmaf(__uint_as_float(v[c + 2]), rstd, bb.z), fmaf(__uint_as_float(v[c + 3]), rstd, bb.w));
-            }
+            ln_apply32(v, hp * 32, rstd, s_beta + half * 64 + hp * 32, zp);
             tmem_st16(lane_addr + Z_COL + half * 32 + hp * 16, zp);
           }
           wait_st();

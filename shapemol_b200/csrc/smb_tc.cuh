@@ -83,6 +83,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 // A failed try_wait returns after a few cycles, so a bare retry loop re-issues twice per ~8 cycles and takes issue
 // slots from the working warps of its scheduler (measured: 35 % of all executed instructions): back off between tries.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+#ifdef SMB_MBAR_SUSPEND_HINT
+  // try_wait with an explicit suspend-time hint: the hardware parks the thread for up to that many nanoseconds
+  asm volatile("{\n\t.reg .pred P1;\n\t"
+               "WAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+               "@!P1 bra WAIT_%=;\n\t"
+               "}\n" :: "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)SMB_MBAR_SUSPEND_HINT) : "memory");
+#else
   asm volatile("{\n\t.reg .pred P1;\n\t"
                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
                "@P1 bra DONE_%=;\n\t"
@@ -91,6 +99,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
                "@!P1 bra WAIT_%=;\n\t"
                "DONE_%=:\n\t}\n" :: "r"(smem_u32(b)), "r"(parity), "r"(20u) : "memory");
+#endif
 }
 // 1-D bulk copy global -> shared (TMA engine); completion is signalled on the mbarrier as `bytes` of transaction count
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -140,6 +149,56 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 #undef SMB_R4
 #undef SMB_W4
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two fp32 operations per issued instruction) ---------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float sum2(uint64_t v) { float lo, hi; upk2(v, lo, hi); return lo + hi; }
+
+// LayerNorm pieces shared by the tcgen05 kernels (affine part folded into the operands, smb_host.cu):
+// sum of squares of 64 accumulator columns, and  z = relu(v * rstd + beta') packed to bf16 pairs.
+__device__ __forceinline__ float ln_sumsq64(const uint32_t (&v)[64]) {
+  uint64_t q0 = 0ull, q1 = 0ull, q2 = 0ull, q3 = 0ull;
+#pragma unroll
+  for (int e = 0; e < 64; e += 8) {
+    const uint64_t p0 = pk2u(v[e], v[e + 1]), p1 = pk2u(v[e + 2], v[e + 3]), p2 = pk2u(v[e + 4], v[e + 5]), p3 = pk2u(v[e + 6], v[e + 7]);
+    q0 = fma2(p0, p0, q0); q1 = fma2(p1, p1, q1); q2 = fma2(p2, p2, q2); q3 = fma2(p3, p3, q3);
+  }
+  return (sum2(q0) + sum2(q1)) + (sum2(q2) + sum2(q3));
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b);
+// 32 columns starting at v[c0] -> 16 packed words; beta points at the 32 floats of these columns (16-byte aligned, smem)
+__device__ __forceinline__ void ln_apply32(const uint32_t (&v)[64], int c0, float rstd, const float* beta, uint32_t (&zp)[16]) {
+  const uint64_t r2 = pk2(rstd, rstd);
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(beta + e);
+    float y0, y1, y2, y3;
+    upk2(fma2(pk2u(v[c0 + e], v[c0 + e + 1]), r2, pk2(bb.x, bb.y)), y0, y1);
+    upk2(fma2(pk2u(v[c0 + e + 2], v[c0 + e + 3]), r2, pk2(bb.z, bb.w)), y2, y3);
+    zp[e / 2] = pack_bf16_relu(y0, y1);
+    zp[e / 2 + 1] = pack_bf16_relu(y2, y3);
+  }
+}
 
 // ---- packed bf16 conversions -----------------------------------------------------------------------
 // (lo16 = bf16(a), hi16 = bf16(b)), round to nearest even, optional fused ReLU
