@@ -90,6 +90,9 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   pa.inv_w1 = fptr(blob, L.inv_w1); pa.inv_b1 = fptr(blob, L.inv_b1); pa.inv_g = fptr(blob, L.inv_g);
   pa.inv_bb = fptr(blob, L.inv_bb); pa.inv_w2 = fptr(blob, L.inv_w2); pa.inv_b2 = fptr(blob, L.inv_b2);
   pa.tau = tau; pa.inv = inv;
+  float* vn_shape = wptr<float>(ws_base, W.vn_shape);
+  pa.n_layers = d.layers; pa.vn_shape = vn_shape;
+  for (int l = 0; l < d.layers; ++l) { pa.vn_w[l][0] = fptr(blob, L.layer[l].vn_feat); pa.vn_w[l][1] = fptr(blob, L.layer[l].vn_dir); }
   SMB_LAUNCH(launch_prep(pa, st));
 
   EmbedArgs ea;
@@ -186,6 +189,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       EdgeArgs e = eb;
       e.col_a = 2 * H; e.col_b = 3 * H;
       e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
+      e.vn_shape = vn_shape + (size_t)l * (B > 0 ? B : 1) * 96;
       fill_edge_weights(e, blob, y.xv);
       SMB_TIMED(SMB_PROF_EDGE_XV, edge(ROLE_XV, e, &bn_rows));
     }

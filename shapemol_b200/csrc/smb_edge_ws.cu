@@ -51,18 +51,27 @@ constexpr int E2_GRP_THREADS = 128;
 constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
 constexpr int GRP_THREADS = GRP_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t Z_COL = 384;
 
 // mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 10, B_E2_DONE = 14, B_AB_FULL = 18, N_BARS = 21 };
-// accumulator ring: ROLE_V keeps z in shared memory, so all 512 TMEM columns hold accumulators
-template <int ROLE> struct Ring { static constexpr int ND = ROLE == ROLE_V ? 4 : 3; };
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14, B_E2_DONE = 22, B_AB_FULL = 30, B_D1_FREE = 33, N_BARS = 35 };
+// TMEM accumulator rings (512 columns in all):
+//   ROLE_K : 3 x 128 (GEMM2 overwrites GEMM1's accumulator in place) + z[2] x 64
+//   ROLE_V : 4 x 128 in place; z lives in shared memory
+//   ROLE_XV: GEMM2 has 16 output columns, so it gets its own ring: D1 2 x 128 | z[2] x 64 | D2 8 x 16.  D1 is free again as
+//            soon as the LayerNorm has read it, and a late epilogue no longer stalls GEMM1.
+template <int ROLE> struct Ring {
+  static constexpr bool SEP = ROLE == ROLE_XV;
+  static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 3;
+  static constexpr int ND2 = SEP ? 8 : ND1;
+  static constexpr uint32_t Z_COL = SEP ? 256 : 384;
+  static constexpr uint32_t D2_COL = SEP ? 384 : 0, D2_STRIDE = SEP ? 16 : 128;
+};
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 21 mbarriers
-  static constexpr int o_tmem = 192;
-  static constexpr int o_vec = 256;               // ln_g | ln_b | b2   (3 x 128 floats)
+  static constexpr int o_bar = 0;                 // 35 mbarriers
+  static constexpr int o_tmem = 288;
+  static constexpr int o_vec = 384;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
   static constexpr int w2_bytes = ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
@@ -110,7 +119,9 @@ __device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
 template <int ROLE>
 __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
   using P = Plan<ROLE>;
-  constexpr int ND = Ring<ROLE>::ND;
+  using R = Ring<ROLE>;
+  constexpr int ND1 = R::ND1, ND2 = R::ND2;
+  constexpr uint32_t Z_COL = R::Z_COL;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::o_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::o_tmem);
@@ -160,12 +171,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       mbar_init(bar + B_A1_FREE + b, 1);
       mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       mbar_init(bar + B_D1_FULL + b, 1);
       mbar_init(bar + B_D2_FULL + b, 1);
       mbar_init(bar + B_E2_DONE + b, E2_GRP_THREADS);
     }
     for (int b = 0; b < 3; ++b) mbar_init(bar + B_AB_FULL + b, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(bar + B_D1_FREE + b, GRP_THREADS);
     mbar_init_fence();
   }
   fence_async_smem();
@@ -274,14 +286,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     float* s_stat = reinterpret_cast<float*>(smem + P::o_stat);
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
-      const int b3 = t % ND, zb = t & 1;
-      mbar_wait(bar + B_D1_FULL + b3, (t / ND) & 1);
+      const int b3 = t % ND1, zb = t & 1;
+      mbar_wait(bar + B_D1_FULL + b3, (t / ND1) & 1);
       fence_after_sync();
       SMB_TRACE(2, t, gw == 0 && lane == 0);
       uint32_t v[64];
       tmem_ld32(lane_addr + b3 * 128 + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(lane_addr + b3 * 128 + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       wait_ld();
+      if (R::SEP) { fence_before_sync(); mbar_arrive(bar + B_D1_FREE + b3); }   // D1 may be overwritten by GEMM1(t + 2)
       // LayerNorm with the affine part folded into the operands (smb_host.cu fold_ln): the accumulator is already
       // centred over the 128 channels and carries sign(gamma), so  z = relu(v * rstd + beta / |gamma|)
       const float sq = ln_sumsq64(v);
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       named_sync(BAR_LN, GRP_THREADS);
       const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
-      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % ND, ((t - 2) / ND) & 1);
+      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % ND2, ((t - 2) / ND2) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
       if (!(a.dbg & 2))
 #pragma unroll
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         for (int p = tg; p < TM * kHeads / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
       }
       if (ROLE == ROLE_XV) {
-        if (tg < kShape * 3 / 4) cp_async16(slot + TM * kHeads * 4 + tg * 16, a.shape + (size_t)T.mol * kShape * 3 + tg * 4);
+        if (tg < 2 * kHeads * 3 / 4) cp_async16(slot + TM * kHeads * 4 + tg * 16, a.vn_shape + (size_t)T.mol * (2 * kHeads * 3) + tg * 4);
         pre_x = pre_y = pre_z = 0.f;
         if (valid) {
           const int i = T.d0 + dl;
@@ -378,19 +391,19 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (t + 2 < nt) stage(t + 2, Tile(td_cur));   // the other slot: its readers (tile t - 2) are behind the trailing barrier
         cp_async_commit();
       }
-      const int b3 = t % ND;
-      const uint32_t dcol = (uint32_t)b3 * 128u;
+      const int b3 = t % ND2;
+      const uint32_t dcol = R::D2_COL + (uint32_t)b3 * R::D2_STRIDE;
       const int rows = T.rows();
       const bool valid = r < rows;
       const int dl = min(T.dst_of(r), NDMAX - 1);
       const unsigned char* slot = es + P::e_stage + (P::n_slots == 2 ? (t >> 1) & 1 : 0) * P::stage_bytes;
       const float* s_q = reinterpret_cast<const float*>(slot);            // ROLE_K
       const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV
-      const float* s_shape = reinterpret_cast<const float*>(slot + TM * kHeads * 4);   // ROLE_XV
+      const float* s_vs = reinterpret_cast<const float*>(slot + TM * kHeads * 4);   // ROLE_XV: shape part of the VN maps [feat | dir][16][3]
 
       if (P::n_slots == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
-      mbar_wait(bar + B_D2_FULL + b3, (t / ND) & 1);
+      mbar_wait(bar + B_D2_FULL + b3, (t / ND2) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
       named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
@@ -555,10 +568,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
             const float wc = w[1 + cc];
             vx = fmaf(wc, so[cc * 4], vx); vy = fmaf(wc, so[cc * 4 + 1], vy); vz = fmaf(wc, so[cc * 4 + 2], vz);
           }
-#pragma unroll 8
-          for (int cc = 0; cc < kShape; ++cc) {
-            const float wc = w[1 + kHeads + cc];
-            vx = fmaf(wc, s_shape[cc * 3], vx); vy = fmaf(wc, s_shape[cc * 3 + 1], vy); vz = fmaf(wc, s_shape[cc * 3 + 2], vz);
+          {   // the shape-embedding channels of z = [x | o | shape_emb] do not depend on the step: prep_kernel contracted them
+            const float* vs = s_vs + (which * kHeads + ch) * 3;
+            vx += vs[0]; vy += vs[1]; vz += vs[2];
           }
           float* row = a.vn + (size_t)(T.a0 + T.d0 + pd) * kVnRow;
           row[3 + which * 48 + ch * 3] = vx; row[4 + which * 48 + ch * 3] = vy; row[5 + which * 48 + ch * 3] = vz;
@@ -619,12 +631,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (t + 3 < nt) td_nx = __ldg(tiles + t + 3);
       mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
       SMB_TRACE(7, t, lane == 0);
-      if (t >= ND) mbar_wait(bar + B_E2_DONE + t % ND, (t / ND - 1) & 1);   // tile t - ND left D[t % ND]
+      if (R::SEP) { if (t >= ND1) mbar_wait(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
+      else if (t >= ND1) mbar_wait(bar + B_E2_DONE + t % ND1, (t / ND1 - 1) & 1);             // tile t - ND1 left D[t % ND1]
       mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(1, t, lane == 0);
       if (lane == 0) {
-        const uint32_t d = tmem + (uint32_t)(t % ND) * 128u;
+        const uint32_t d = tmem + (uint32_t)(t % ND1) * 128u;
         const uint32_t a1 = a1_base + (t & 1) * A1_BYTES;
         const uint32_t ab = ab_base + (t % 3) * AB_BYTES;
         const uint32_t sbo_ab = (uint32_t)(td_cur.z & 0xff) * 16u;   // n * 16: column-group stride of the projection tiles
@@ -635,7 +648,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(ab + (ks >> 2) * (G * H * 2) + (ks & 1) * 256, 128, sbo_ab), IDESC1, 1);
         SMB_TRACE(8, t, true);
         mma_commit(bar + B_A1_FREE + (t & 1));
-        mma_commit(bar + B_D1_FULL + t % ND);
+        mma_commit(bar + B_D1_FULL + t % ND1);
         SMB_TRACE(9, t, true);
       }
       __syncwarp();
@@ -656,10 +669,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     for (int u = 0; u < nt; ++u) {
       const int zb = u & 1;
       mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
+      if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + u % ND2, (u / ND2 - 1) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
       fence_after_sync();
       SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {
-        const uint32_t d = tmem + (uint32_t)(u % ND) * 128u;
+        const uint32_t d = tmem + R::D2_COL + (uint32_t)(u % ND2) * R::D2_STRIDE;
         if (ROLE == ROLE_V) {
           const uint32_t zt = smem_u32(smem + P::o_z + zb * (TM * H * 2));
 #pragma unroll
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           for (int ks = 0; ks < H / 16; ++ks)
             mma_ts(d, tmem + Z_COL + zb * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
         }
-        mma_commit(bar + B_D2_FULL + u % ND);
+        mma_commit(bar + B_D2_FULL + u % ND2);
       }
       __syncwarp();
     }

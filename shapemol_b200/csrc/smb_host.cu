@@ -135,6 +135,7 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.bn_part_rows = kEdgeMaxCtas * kEdgeWarps;
   w.bn_part = c.take((size_t)w.bn_part_rows * 32 * 4);
   w.bn_param = c.take(32 * 4);
+  w.vn_shape = c.take((size_t)d.layers * b * 96 * 4);
   w.tiles = c.take(16 + (size_t)w.max_tiles * 16);
   w.total = c.off;
   return w;

@@ -15,6 +15,11 @@ struct PrepArgs {
   const float *inv_w1, *inv_b1, *inv_g, *inv_bb, *inv_w2, *inv_b2;
   float* tau;              // [B,8]
   float* inv;              // [B,32]
+  // shape-embedding part of every layer's VN linear maps (BaseH2XAttLayer.shape_linear, uni_transformer.py:153-156):
+  // vn_shape[l][m][feat | dir][16][3] = sum_c W_l[ch][17 + c] * shape[m][c][:]   (constant over the layer's atoms)
+  int n_layers;
+  const float* vn_w[kMaxLayers][2];   // map_to_feat / map_to_dir weights [16][49]
+  float* vn_shape;         // [L][B][96] or NULL
 };
 
 struct EmbedArgs {
@@ -104,6 +109,7 @@ struct EdgeArgs {
   // ROLE_XV
   const float* shape;      // [B][32][3]
   const float *vn_feat, *vn_dir;   // [16][49]
+  const float* vn_shape;   // [B][96] this layer's slice of PrepArgs::vn_shape (warp-specialised pipeline)
   float* vn;               // [N][kVnRow]
   float* bn_partial;       // [gridDim.x*warps][32]
   // weights

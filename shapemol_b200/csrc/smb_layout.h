@@ -105,6 +105,7 @@ struct Workspace {
   size_t vn;        // [N][100]  (o_mean 3 | p 48 | d 48 | pad)
   size_t bn_part;   // [bn_part_rows][32]
   size_t bn_param;  // [32] scale | shift
+  size_t vn_shape;  // [L][B][96] shape-embedding part of the VN linear maps
   size_t tiles;     // [max_tiles] int4 tile descriptors, preceded by the tile count (16 bytes)
   int max_tiles;    // N/4 + B + 8: a tile holds >= 4 destination atoms unless it is the last of its molecule
   int bn_part_rows;

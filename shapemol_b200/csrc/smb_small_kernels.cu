@@ -63,6 +63,23 @@ __global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
 #pragma unroll 8
     for (int c = 0; c < 32; ++c) o = fmaf(a.inv_w2[lane * 32 + c], __shfl_sync(0xffffffffu, z, c), o);
     a.inv[m * kShape + lane] = o;
+    // ---- shape part of the VN linear maps: lane = (feat | dir, channel), three components each ----
+    if (a.vn_shape) {
+      const int which = lane >> 4, ch = lane & 15;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const float* w = a.vn_w[l][which] + ch * kVnStride + 1 + kHeads;
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < kShape; ++c) {
+          const float wc = __ldg(w + c);
+          vx = fmaf(wc, __shfl_sync(0xffffffffu, sx, c), vx);
+          vy = fmaf(wc, __shfl_sync(0xffffffffu, sy, c), vy);
+          vz = fmaf(wc, __shfl_sync(0xffffffffu, sz, c), vz);
+        }
+        float* o3 = a.vn_shape + ((size_t)l * a.n_mols + m) * 96 + lane * 3;
+        o3[0] = vx; o3[1] = vy; o3[2] = vz;
+      }
+    }
   }
 }
 
