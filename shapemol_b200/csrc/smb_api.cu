@@ -164,7 +164,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       n.x_mode = XMODE_AGG_H; n.act = ACT_LN_RELU; n.n_pass = 0; n.n2 = H; n.n2_valid = H;
       n.xa = agg; n.xb = h_in; n.residual = h_in; n.out2 = h_out;
       fill_node_weights(n, blob, y.node_out);
-      SMB_TIMED(SMB_PROF_NODE_OUT, launch_node_mlp(d, n, st));
+      SMB_TIMED(SMB_PROF_NODE_OUT, node_tc5 ? launch_node_out_tc5(n, st) : launch_node_mlp(d, n, st));
     }
     // ---- H2X (uses the updated h) ----
     {

@@ -112,7 +112,7 @@ struct Tile {
 };
 
 // timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
-constexpr int TRACE_EVENTS = 12, TRACE_TILES = 128;
+constexpr int TRACE_EVENTS = 13, TRACE_TILES = 128;
 __device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
 #define SMB_TRACE(ev, t, cond) do { if ((a.dbg & 16) && (a.dbg >> 8) == ROLE && blockIdx.x == 0 && (t) < TRACE_TILES && (cond)) g_trace[ev][t] = clock64(); } while (0)
 
@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(7, t, lane == 0);
       if (R::SEP) { if (t >= ND1) mbar_wait(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
       else if (t >= ND1) mbar_wait(bar + B_E2_DONE + t % ND1, (t / ND1 - 1) & 1);             // tile t - ND1 left D[t % ND1]
+      SMB_TRACE(12, t, lane == 0);
       mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(1, t, lane == 0);

@@ -54,7 +54,7 @@ EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
   e.beta_f = gate ? e.ln_b : c.take(H * 4);
   return e;
 }
-NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2, bool folded = false) {
+NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2, bool folded = false, bool out_tc5 = false) {
   const int H = d.hidden;
   const size_t fb = frag_bytes(d);
   NodeMlpOff n;
@@ -69,6 +69,11 @@ NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2
   n.w1_t = folded ? c.take((size_t)5 * kNodeChunkBytes) : n.w1;
   n.w2_t = folded ? c.take((size_t)H * H * 2) : n.w2;
   n.beta_t = folded ? c.take(H * 4) : n.ln_b;
+  if (out_tc5) {
+    n.w1_t = c.take((size_t)128 * kNodeOutKx * 2);
+    n.w2_t = c.take((size_t)H * H * 2);
+    n.beta_t = c.take(H * 4);
+  }
   return n;
 }
 }  // namespace
@@ -100,7 +105,7 @@ ModelLayout build_layout(const smb_model_dims& d) {
     y.xk = carve_edge(c, d, H, false);
     y.xv = carve_edge(c, d, kHeads, false);
     y.x2h_pre = carve_node(c, d, 5 * H, H + kShape, H, true);
-    y.node_out = carve_node(c, d, H, 2 * H, H);
+    y.node_out = carve_node(c, d, H, 2 * H, H, false, true);
     y.h2x_pre = carve_node(c, d, 5 * H, H + kShape, H, true);
     y.vn_feat = c.take(kHeads * kVnStride * 4);
     y.vn_dir = c.take(kHeads * kVnStride * 4);
@@ -406,6 +411,33 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
       put(blob, y.node_out.ln_b, get(p + ".net.1.bias"), H);
       pack_frags(blob + y.node_out.w2, H / 8, H / 16, prec, [&](int n, int k) { return w2[(size_t)n * H + k]; });
       put(blob, y.node_out.b2, get(p + ".net.3.bias"), H);
+      // tcgen05 images (node_tc5_kernel<1>): LayerNorm-folded first Linear [128 n][272 k] with the bias in k = 256 / 257
+      const Fold fo = make_fold(p);
+      const float* b1 = get(p + ".net.0.bias");
+      uint16_t* wt = reinterpret_cast<uint16_t*>(blob + y.node_out.w1_t);
+      auto at = [&](int nn, int k) -> uint16_t& {
+        return wt[((size_t)(nn / 8) * (kNodeOutKx / 8) * 128 + (size_t)(k / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2) / 2];
+      };
+      for (int k = 0; k < 2 * H; ++k) {
+        double m = 0.0;
+        for (int r = 0; r < H; ++r) m += w1[(size_t)r * 2 * H + k];
+        m /= H;
+        for (int r = 0; r < H; ++r) at(r, k) = f2bf(fo.f[r] * (float)((double)w1[(size_t)r * 2 * H + k] - m));
+      }
+      double mb = 0.0;
+      for (int r = 0; r < H; ++r) mb += b1[r];
+      mb /= H;
+      for (int r = 0; r < H; ++r) {
+        const float b = fo.f[r] * (float)((double)b1[r] - mb);
+        const uint16_t hi = f2bf(b);
+        at(r, 2 * H) = hi;
+        at(r, 2 * H + 1) = f2bf(b - bf2f(hi));
+      }
+      uint16_t* w2t = reinterpret_cast<uint16_t*>(blob + y.node_out.w2_t);
+      for (int nn = 0; nn < H; ++nn)
+        for (int k = 0; k < H; ++k)
+          w2t[((size_t)(nn / 8) * 2048 + (size_t)(k / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2[(size_t)nn * H + k] * fo.mag[k]);
+      put(blob, y.node_out.beta_t, fo.beta.data(), H);
     }
     put(blob, y.vn_feat, get(h2x + "shape_linear.map_to_feat.weight"), kHeads * kVnIn);
     put(blob, y.vn_dir, get(h2x + "shape_linear.map_to_dir.weight"), kHeads * kVnIn);

@@ -84,12 +84,15 @@ struct NodeArgs {
   const int* mol_ptr;
   float* out2;             // [N][n2_valid]
   const void *w1_t, *w2_t; const float* beta_t;   // tcgen05 operand images (NodeMlpOff::w1_t / w2_t / beta_t)
+  int dbg;                 // SMB_NODE_DBG bit mask (timing experiments only: results are wrong when set)
 };
 int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);
 // tcgen05 implementation of XMODE_H_INV for the warp-specialised edge pipeline (smb_node_tc5.cu): needs out1_h,
 // mol_ptr, w1_t, w2_t, beta_t, b2
 bool node_tc5_supported(const smb_model_dims& d, int n_max);
 int launch_node_pre_tc5(const NodeArgs& a, cudaStream_t st);
+// XMODE_AGG_H (node_output MLP + residual): needs w1_t, w2_t, beta_t, b2, residual
+int launch_node_out_tc5(const NodeArgs& a, cudaStream_t st);
 
 // Edge kernels (smb_edge_attn.cu)
 enum EdgeRole { ROLE_GATE = 0, ROLE_K = 1, ROLE_V = 2, ROLE_XV = 3 };

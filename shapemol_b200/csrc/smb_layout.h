@@ -49,7 +49,8 @@ struct NodeMlpOff {
   // x2h_pre / h2x_pre only: W1 / b1 with the four pass-through blocks LayerNorm-folded like EdgeMlpOff::w1r_f
   size_t w1_f;
   size_t b1_f;
-  // x2h_pre / h2x_pre only: tcgen05 operand images for node_pre_tc5_kernel (smb_node_tc5.cu).  Every block is
+  // x2h_pre / h2x_pre / node_out: tcgen05 operand images for node_tc5_kernel (smb_node_tc5.cu); node_out has the
+  // hidden block only, [128 n][kNodeOutKx k].  Every block is
   // LayerNorm-folded (the four pass-through blocks with their edge MLP's LayerNorm, the hidden block with the query
   // MLP's); the bias rides in two extra K columns (bf16 hi | lo) against constant-one activations.
   size_t w1_t;   // 5 chunks [hidden | A_k | B_k | A_v | B_v] of [128 n][kNodeKx k] bf16, K-major:
@@ -59,6 +60,7 @@ struct NodeMlpOff {
 };
 constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
 constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
+constexpr int kNodeOutKx = 272;                         // node_output: 128 (agg) + 128 (h) + 16 (bias hi | bias lo | zeros)
 
 struct LayerOff {
   EdgeMlpOff hk, hv, xk, xv;

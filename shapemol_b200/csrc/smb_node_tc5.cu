@@ -25,11 +25,6 @@ namespace {
 using namespace tc;
 
 constexpr int H = 128, TM = 128;
-constexpr int KX = kNodeKx;                  // 176
-constexpr int X_SBO = (KX / 8) * 128;        // 2816
-constexpr int X_BYTES = TM * KX * 2;         // 45056
-constexpr int WCH_BYTES = kNodeChunkBytes;   // 45056
-constexpr int N_CH = 5;                      // hidden | A_k | B_k | A_v | B_v
 constexpr int W2_BYTES = H * H * 2;
 constexpr int W_WARP = 0, MMA_WARP = 1, X_WARP0 = 2, X_WARPS = 4, E_WARP0 = 6, E_WARPS = 8, WARPS = 14, THREADS = WARPS * 32;
 constexpr int E_THREADS = E_WARPS * 32, X_THREADS = X_WARPS * 32;
@@ -38,18 +33,37 @@ constexpr uint32_t Z_COL = 384;
 
 enum { B_X_FULL = 0, B_X_FREE = 2, B_W_FULL = 4, B_W_FREE = 6, B_D_FULL = 8, B_D_FREE = 11, B_Z_FULL = 14, N_BARS = 15 };
 
-constexpr int o_bar = 0;
-constexpr int o_tmem = 128;
-constexpr int o_beta = 256;                  // beta / |gamma| of the query MLP's LayerNorm
-constexpr int o_b2 = o_beta + 512;
-constexpr int o_stat = o_b2 + 512;           // float[2 tiles][2 halves][128 rows]
-constexpr int o_w2 = o_stat + 2048;          // 3328 -> aligned 128
-constexpr int o_x = o_w2 + W2_BYTES;
-constexpr int o_w = o_x + 2 * X_BYTES;
-constexpr int SMEM_TOTAL = o_w + 2 * WCH_BYTES;
-static_assert(o_w2 % 128 == 0 && SMEM_TOTAL <= 227 * 1024, "shared memory plan");
+// MODE 0 (pre): X = [h | inv | 1 1 0..] (K = 176), five streamed weight chunks, two X slots; accumulator productions per
+//               tile: hidden, A_k, B_k, A_v, B_v, GEMM2 (q)
+// MODE 1 (out): X = [agg | h | 1 1 0..] (K = 272), node_output MLP (uni_transformer.py:82,87-88): one resident weight
+//               block, one X slot; productions per tile: hidden, GEMM2 (+ b2 + residual h -> h')
+template <int MODE>
+struct Cfg {
+  static constexpr int KX = MODE == 0 ? kNodeKx : kNodeOutKx;
+  static constexpr int X_SBO = (KX / 8) * 128;
+  static constexpr int X_BYTES = TM * KX * 2;
+  static constexpr int WCH_BYTES = 128 * KX * 2;
+  static constexpr int N_CH = MODE == 0 ? 5 : 1;
+  static constexpr int NXS = MODE == 0 ? 2 : 1, NWS = MODE == 0 ? 2 : 1;
+  static constexpr int STEPS = MODE == 0 ? 6 : 2, G2_STEP = MODE == 0 ? 5 : 1;   // GEMM2 last: the MMA warp never waits for the LayerNorm
+  static constexpr int o_bar = 0;
+  static constexpr int o_tmem = 128;
+  static constexpr int o_beta = 256;                  // beta / |gamma| of the LayerNorm
+  static constexpr int o_b2 = o_beta + 512;
+  static constexpr int o_stat = o_b2 + 512;           // float[2 tiles][2 halves][128 rows]
+  static constexpr int o_w2 = o_stat + 2048;          // 3328
+  static constexpr int o_x = o_w2 + W2_BYTES;
+  static constexpr int o_w = o_x + NXS * X_BYTES;
+  static constexpr int SMEM_TOTAL = o_w + NWS * WCH_BYTES;
+  static_assert(o_w2 % 128 == 0 && SMEM_TOTAL <= 227 * 1024, "shared memory plan");
+};
 
-__global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
+  using C = Cfg<MODE>;
+  constexpr int KX = C::KX, X_SBO = C::X_SBO, X_BYTES = C::X_BYTES, WCH_BYTES = C::WCH_BYTES, N_CH = C::N_CH;
+  constexpr int NXS = C::NXS, NWS = C::NWS, STEPS = C::STEPS, G2_STEP = C::G2_STEP;
+  constexpr int o_bar = C::o_bar, o_tmem = C::o_tmem, o_beta = C::o_beta, o_b2 = C::o_b2, o_stat = C::o_stat, o_w2 = C::o_w2, o_x = C::o_x, o_w = C::o_w;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + o_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + o_tmem);
@@ -72,12 +86,12 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
     if (tid < H) { s_beta[tid] = a.beta_t[tid]; s_b2[tid] = a.b2[tid]; }
     // operand slots start at zero; the constant-one bias columns (k = 160, 161) are written once
     uint4* z0 = reinterpret_cast<uint4*>(s_x);
-    for (int p = tid; p < 2 * X_BYTES / 16; p += THREADS) z0[p] = make_uint4(0u, 0u, 0u, 0u);
+    for (int p = tid; p < NXS * X_BYTES / 16; p += THREADS) z0[p] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  for (int p = tid; p < 2 * TM; p += THREADS) {
+  for (int p = tid; p < NXS * TM; p += THREADS) {
     const int slot = p >> 7, r = p & 127;
-    *reinterpret_cast<uint32_t*>(s_x + slot * X_BYTES + (r >> 3) * X_SBO + (160 / 8) * 128 + (r & 7) * 16) = 0x3F803F80u;
+    *reinterpret_cast<uint32_t*>(s_x + slot * X_BYTES + (r >> 3) * X_SBO + ((KX - 16) / 8) * 128 + (r & 7) * 16) = 0x3F803F80u;
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid == 32) {
@@ -104,11 +118,12 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
     // =========================== weight chunks: L2 -> smem ring ===========================
     if (lane == 0) {
       const unsigned char* src = reinterpret_cast<const unsigned char*>(a.w1_t);
-      const int jobs = nt * N_CH;
+      const int jobs = MODE == 0 ? nt * N_CH : (nt > 0 ? 1 : 0);   // MODE 1: the single weight block stays resident
       int c = 0;
       for (int j = 0; j < jobs; ++j) {
-        const int slot = j & 1;
-        if (j >= 2) mbar_wait(bar + B_W_FREE + slot, ((j >> 1) - 1) & 1);
+        const int slot = j % NWS;
+        if (j >= NWS) mbar_wait(bar + B_W_FREE + slot, ((j / NWS) - 1) & 1);
+        if ((a.dbg & 1) && j >= NWS) { mbar_arrive(bar + B_W_FULL + slot); c = c + 1 == N_CH ? 0 : c + 1; continue; }   // timing: no weight streaming
         mbar_arrive_expect_tx(bar + B_W_FULL + slot, WCH_BYTES);
         bulk_g2s(s_w + slot * WCH_BYTES, src + (size_t)c * WCH_BYTES, WCH_BYTES, bar + B_W_FULL + slot);
         c = c + 1 == N_CH ? 0 : c + 1;
@@ -119,77 +134,86 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
     constexpr uint32_t IDESC = idesc_bf16(H, false);
     const uint32_t x_base = smem_u32(s_x), w_base = smem_u32(s_w), w2_base = smem_u32(s_w2);
     int g = 0, j = 0;
+    if (MODE == 1 && nt > 0) mbar_wait(bar + B_W_FULL, 0);
 #pragma unroll 1
     for (int it = 0; it < nt; ++it) {
-      const int xs = it & 1;
-      mbar_wait(bar + B_X_FULL + xs, (it >> 1) & 1);
+      const int xs = it % NXS;
+      mbar_wait(bar + B_X_FULL + xs, (it / NXS) & 1);
 #pragma unroll 1
-      for (int s = 0; s < 6; ++s, ++g) {
+      for (int s = 0; s < STEPS; ++s, ++g) {
         const int db = g % 3;
         const uint32_t d = tmem + (uint32_t)db * 128u;
-        if (s != 3) mbar_wait(bar + B_W_FULL + (j & 1), (j >> 1) & 1);
-        else mbar_wait(bar + B_Z_FULL, it & 1);
+        if (s == G2_STEP) mbar_wait(bar + B_Z_FULL, it & 1);
+        else if (MODE == 0) mbar_wait(bar + B_W_FULL + (j & 1), (j >> 1) & 1);
         if (g >= 3) mbar_wait(bar + B_D_FREE + db, (g / 3 - 1) & 1);
         fence_after_sync();
         if (lane == 0) {
-          if (s != 3) {
-            const uint32_t xa = x_base + xs * X_BYTES, wb = w_base + (j & 1) * WCH_BYTES;
+          if (s != G2_STEP) {
+            const uint32_t xa = x_base + xs * X_BYTES, wb = w_base + (MODE == 0 ? (j & 1) : 0) * WCH_BYTES;
 #pragma unroll
             for (int ks = 0; ks < KX / 16; ++ks)
               mma_ss(d, smem_desc(xa + ks * 256, 128, X_SBO), smem_desc(wb + ks * 256, 128, X_SBO), IDESC, ks > 0);
-            mma_commit(bar + B_W_FREE + (j & 1));
+            if (MODE == 0) mma_commit(bar + B_W_FREE + (j & 1));
           } else {
 #pragma unroll
             for (int ks = 0; ks < H / 16; ++ks)
               mma_ts(d, tmem + Z_COL + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC, ks > 0);
           }
           mma_commit(bar + B_D_FULL + db);
-          if (s == 5) mma_commit(bar + B_X_FREE + xs);
+          if (s == (MODE == 0 ? STEPS - 2 : 0)) mma_commit(bar + B_X_FREE + xs);   // last GEMM that reads this X slot
         }
         __syncwarp();
-        if (s != 3) ++j;
+        if (s != G2_STEP) ++j;
       }
     }
   } else if (warp < E_WARP0) {
     // =========================== X tiles: fp32 -> bf16 operand layout ===========================
     const int xw = warp - X_WARP0;
     const int rr = lane & 7, kq = lane >> 3;
+    constexpr int KSTEPS = MODE == 0 ? 5 : 8;          // groups of 4 x (8 columns) per row: 128 h + 32 inv | 128 agg + 128 h
 #pragma unroll 1
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      const int xs = it & 1;
+      const int xs = it % NXS;
       unsigned char* xb = s_x + xs * X_BYTES;
       int mol[4];
 #pragma unroll
       for (int rb = 0; rb < 4; ++rb) {
         const int grow = tile * TM + xw * 32 + rb * 8 + rr;
-        mol[rb] = grow < a.n_atoms ? __ldg(a.atom_mol + grow) : -1;
+        mol[rb] = grow < a.n_atoms ? (MODE == 0 ? __ldg(a.atom_mol + grow) : 0) : -1;
       }
-      if (it >= 2) mbar_wait(bar + B_X_FREE + xs, ((it >> 1) - 1) & 1);
+      if (it >= NXS) mbar_wait(bar + B_X_FREE + xs, ((it / NXS) - 1) & 1);
+      constexpr int RPB = MODE == 0 ? 2 : 1;           // row blocks in flight per thread (register budget)
 #pragma unroll
-      for (int rp = 0; rp < 2; ++rp) {
-        float4 v[2][5][2];
+      for (int rp = 0; rp < 4 / RPB; ++rp) {
+        float4 v[RPB][KSTEPS][2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int rb = rp * 2 + q;
+        for (int q = 0; q < RPB; ++q) {
+          const int rb = rp * RPB + q;
           const int grow = tile * TM + xw * 32 + rb * 8 + rr;
-          if (mol[rb] >= 0) {
+          if (mol[rb] >= 0 && !(a.dbg & 4)) {
             const float4* hp = reinterpret_cast<const float4*>(a.xa + (size_t)grow * H + kq * 8);
 #pragma unroll
             for (int st = 0; st < 4; ++st) { v[q][st][0] = __ldg(hp + st * 8); v[q][st][1] = __ldg(hp + st * 8 + 1); }
-            const float4* ip = reinterpret_cast<const float4*>(a.xb + (size_t)mol[rb] * kShape + kq * 8);
-            v[q][4][0] = __ldg(ip); v[q][4][1] = __ldg(ip + 1);
+            if (MODE == 0) {
+              const float4* ip = reinterpret_cast<const float4*>(a.xb + (size_t)mol[rb] * kShape + kq * 8);
+              v[q][4][0] = __ldg(ip); v[q][4][1] = __ldg(ip + 1);
+            } else {
+              const float4* h2 = reinterpret_cast<const float4*>(a.xb + (size_t)grow * H + kq * 8);
+#pragma unroll
+              for (int st = 0; st < 4; ++st) { v[q][4 + st][0] = __ldg(h2 + st * 8); v[q][4 + st][1] = __ldg(h2 + st * 8 + 1); }
+            }
           } else {
 #pragma unroll
-            for (int st = 0; st < 5; ++st) v[q][st][0] = v[q][st][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int st = 0; st < KSTEPS; ++st) v[q][st][0] = v[q][st][1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int r = xw * 32 + (rp * 2 + q) * 8 + rr;
+        for (int q = 0; q < RPB; ++q) {
+          const int r = xw * 32 + (rp * RPB + q) * 8 + rr;
           unsigned char* row = xb + (r >> 3) * X_SBO + (r & 7) * 16;
 #pragma unroll
-          for (int st = 0; st < 5; ++st) {
+          for (int st = 0; st < KSTEPS; ++st) {
             const int kg = st * 4 + kq;
             const float4 lo = v[q][st][0], hi = v[q][st][1];
             *reinterpret_cast<uint4*>(row + kg * 128) =
@@ -214,10 +238,10 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
       const int grow = tile * TM + r;
       const bool valid = grow < a.n_atoms;
       int ma = 0, mn = 1;
-      if (valid) { const int m = __ldg(a.atom_mol + grow); ma = __ldg(a.mol_ptr + m); mn = __ldg(a.mol_ptr + m + 1) - ma; }
+      if (MODE == 0 && valid) { const int m = __ldg(a.atom_mol + grow); ma = __ldg(a.mol_ptr + m); mn = __ldg(a.mol_ptr + m + 1) - ma; }
       unsigned char* img_row = img + (size_t)ma * 1024 + (size_t)(grow - ma) * 16;
 #pragma unroll 1
-      for (int s = 0; s < 6; ++s, ++g) {
+      for (int s = 0; s < STEPS; ++s, ++g) {
         const int db = g % 3;
         mbar_wait(bar + B_D_FULL + db, (g / 3) & 1);
         fence_after_sync();
@@ -243,18 +267,20 @@ __global__ void __launch_bounds__(THREADS, 1) node_pre_tc5_kernel(NodeArgs a) {
           wait_st();
           fence_before_sync();
           mbar_arrive(bar + B_Z_FULL);
-        } else if (s == 3) {
-          if (valid) {
+        } else if (s == G2_STEP) {
+          if (valid && !(a.dbg & 2)) {
             float4* dst = reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
+            const float4* res = MODE == 1 ? reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64) : nullptr;
 #pragma unroll
             for (int e = 0; e < 64; e += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(s_b2 + half * 64 + e);
+              float4 bb = *reinterpret_cast<const float4*>(s_b2 + half * 64 + e);
+              if (MODE == 1) { const float4 rv = __ldg(res + e / 4); bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w; }
               dst[e / 4] = make_float4(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y, __uint_as_float(v[e + 2]) + bb.z,
                                        __uint_as_float(v[e + 3]) + bb.w);
             }
           }
-        } else if (valid) {
-          const int part = s < 3 ? s - 1 : s - 2;
+        } else if (MODE == 0 && valid && !(a.dbg & 2)) {
+          const int part = s - 1;
           unsigned char* dst = img_row + (size_t)part * mn * 256 + (size_t)(half * 8) * mn * 16;
 #pragma unroll
           for (int cg = 0; cg < 8; ++cg) {
@@ -280,12 +306,13 @@ bool node_tc5_supported(const smb_model_dims& d, int n_max) {
   return !off && edge_ws_supported(d, n_max);
 }
 
-int launch_node_pre_tc5(const NodeArgs& a, cudaStream_t st) {
+template <int MODE>
+static int launch_tc5(const NodeArgs& a, cudaStream_t st) {
   if (a.n_atoms <= 0) return 0;
   static bool configured = false;
   static int n_sm = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(node_pre_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(node_tc5_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::SMEM_TOTAL);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) n_sm = n;
@@ -293,8 +320,14 @@ int launch_node_pre_tc5(const NodeArgs& a, cudaStream_t st) {
   }
   const int n_tiles = (a.n_atoms + TM - 1) / TM;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  node_pre_tc5_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(a);
+  static const int dbg = getenv("SMB_NODE_DBG") ? atoi(getenv("SMB_NODE_DBG")) : 0;
+  NodeArgs b = a;
+  b.dbg = dbg;
+  node_tc5_kernel<MODE><<<grid, THREADS, Cfg<MODE>::SMEM_TOTAL, st>>>(b);
   return (int)cudaGetLastError();
 }
+
+int launch_node_pre_tc5(const NodeArgs& a, cudaStream_t st) { return launch_tc5<0>(a, st); }
+int launch_node_out_tc5(const NodeArgs& a, cudaStream_t st) { return launch_tc5<1>(a, st); }
 
 }  // namespace smb

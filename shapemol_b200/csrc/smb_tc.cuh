@@ -101,6 +101,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                "DONE_%=:\n\t}\n" :: "r"(smem_u32(b)), "r"(parity), "r"(20u) : "memory");
 #endif
 }
+// busy-polling variant for the single MMA-issuer warps: their wake-up latency is on every tile's critical path
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\t"
+               "WAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+               "@!P1 bra WAIT_%=;\n\t"
+               "}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
 // 1-D bulk copy global -> shared (TMA engine); completion is signalled on the mbarrier as `bytes` of transaction count
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
