@@ -110,7 +110,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   int* n_tiles = wptr<int>(ws_base, W.tiles);
   if (ws) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
   auto edge = [&](int role, const EdgeArgs& e, int* bn_rows) -> int {
-    return ws && role != ROLE_GATE ? launch_edge_ws(role, e, bn_rows, st) : launch_edge(d, role, e, bn_rows, st);
+    return ws ? launch_edge_ws(role, e, bn_rows, st) : launch_edge(d, role, e, bn_rows, st);
   };
 
   EdgeArgs eb;
@@ -123,7 +123,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   {  // global edge gate, computed once from the input coordinates (uni_transformer.py:507)
     EdgeArgs e = eb;
     fill_edge_weights(e, blob, L.gate);
-    SMB_TIMED(SMB_PROF_GATE, launch_edge(d, ROLE_GATE, e, nullptr, st));
+    SMB_TIMED(SMB_PROF_GATE, edge(ROLE_GATE, e, nullptr));
   }
 
   int cur = 0;

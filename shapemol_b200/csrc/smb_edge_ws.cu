@@ -60,7 +60,7 @@ enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14
 //   ROLE_XV: GEMM2 has 16 output columns, so it gets its own ring: D1 2 x 128 | z[2] x 64 | D2 8 x 16.  D1 is free again as
 //            soon as the LayerNorm has read it, and a late epilogue no longer stalls GEMM1.
 template <int ROLE> struct Ring {
-  static constexpr bool SEP = ROLE == ROLE_XV;
+  static constexpr bool SEP = ROLE == ROLE_XV || ROLE == ROLE_GATE;   // ROLE_GATE has no GEMM2 at all
   static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 3;
   static constexpr int ND2 = SEP ? 8 : ND1;
   static constexpr uint32_t Z_COL = SEP ? 256 : 384;
@@ -74,7 +74,7 @@ struct Plan {
   static constexpr int o_vec = 384;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
-  static constexpr int w2_bytes = ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
+  static constexpr int w2_bytes = ROLE == ROLE_GATE ? 0 : ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
   static constexpr int o_a1 = o_w2 + w2_bytes;    // 2 slots
   static constexpr int o_ab = o_a1 + 2 * A1_BYTES;   // 3 slots
   static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float2[2 buffers][2 halves][128]
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     uint4* d2 = reinterpret_cast<uint4*>(s_w2);
     for (int p = tid; p < P::w2_bytes / 16; p += THREADS) d2[p] = s2[p];
     if (tid < H) {
-      s_g[tid] = 0.f;
+      s_g[tid] = ROLE == ROLE_GATE ? reinterpret_cast<const float*>(a.w2_f)[tid] : 0.f;   // ROLE_GATE: second Linear (a vector) x |gamma|
       s_be[tid] = a.beta_f[tid];   // beta / |gamma| (LayerNorm folded into the weight images)
-      s_b2[tid] = ROLE == ROLE_XV ? (tid < kHeads ? a.b2[tid] : 0.f) : a.b2[tid];
+      s_b2[tid] = ROLE == ROLE_GATE ? a.b2[0] : ROLE == ROLE_XV ? (tid < kHeads ? a.b2[tid] : 0.f) : a.b2[tid];
     }
     if (ROLE == ROLE_XV)
       for (int p = tid; p < kHeads * kVnStride; p += THREADS) {
@@ -260,8 +260,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           *reinterpret_cast<uint4*>(arow) = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
           *reinterpret_cast<uint4*>(arow + 128) =
               make_uint4(pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
-          *reinterpret_cast<uint4*>(arow + 256) = make_uint4(pack_bf16(e[16], e[17]), pack_bf16(e[18], e[19]), 0u, 0u);
+          // ROLE_GATE: k = 20, 21 are constant ones against the bias rows (hi | lo) of the folded first Linear
+          *reinterpret_cast<uint4*>(arow + 256) = make_uint4(pack_bf16(e[16], e[17]), pack_bf16(e[18], e[19]), ROLE == ROLE_GATE ? 0x3F803F80u : 0u, 0u);
           // one-hot(dst) in k = 32..63, one-hot(src) in k = 64..95: clear this row's previous one, set the new one
+          if (ROLE != ROLE_GATE) {
           const uint32_t oi = (uint32_t)((4 + (i[u] >> 3)) * 128 + (i[u] & 7) * 2);
           const uint32_t oj = (uint32_t)((8 + (j[u] >> 3)) * 128 + (j[u] & 7) * 2);
           *reinterpret_cast<uint16_t*>(arow + (slot ? old_i[1][u] : old_i[0][u])) = 0;
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           *reinterpret_cast<uint16_t*>(arow + oi) = 0x3F80;
           *reinterpret_cast<uint16_t*>(arow + oj) = 0x3F80;
           if (slot) { old_i[1][u] = oi; old_j[1][u] = oj; } else { old_i[0][u] = oi; old_j[0][u] = oj; }
+          }
         }
       }
       fence_async_smem();
@@ -302,6 +305,30 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       st[half * TM + r] = sq;
       named_sync(BAR_LN, GRP_THREADS);
       const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
+      if (ROLE == ROLE_GATE) {
+        // e_w = sigmoid(w2 . relu(LN(.)) + b2)   (uni_transformer.py:475-481): each half-row thread dots its 64 columns
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_be + half * 64 + e);
+          const float4 ww = *reinterpret_cast<const float4*>(s_g + half * 64 + e);
+          dot = fmaf(fmaxf(fmaf(__uint_as_float(v[e]), rstd, bb.x), 0.f), ww.x, dot);
+          dot = fmaf(fmaxf(fmaf(__uint_as_float(v[e + 1]), rstd, bb.y), 0.f), ww.y, dot);
+          dot = fmaf(fmaxf(fmaf(__uint_as_float(v[e + 2]), rstd, bb.z), 0.f), ww.z, dot);
+          dot = fmaf(fmaxf(fmaf(__uint_as_float(v[e + 3]), rstd, bb.w), 0.f), ww.w, dot);
+        }
+        float* sd = reinterpret_cast<float*>(smem + P::o_e2) + zb * (2 * TM);
+        sd[half * TM + r] = dot;
+        named_sync(BAR_LN, GRP_THREADS);
+        if (half == 0) {
+          const Tile T(__ldg(tiles + t));
+          if (r < T.rows()) {
+            const int dl = T.dst_of(r);
+            a.ew_out[(size_t)(T.a0 + T.d0 + dl) * KSTR + (r - dl * T.deg)] = 1.f / (1.f + __expf(-(dot + sd[TM + r] + s_b2[0])));
+          }
+        }
+        continue;
+      }
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
       if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % ND2, ((t - 2) / ND2) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
@@ -326,6 +353,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(3, t, gw == 0 && lane == 0);
       mbar_arrive(bar + B_Z_FULL + zb);
     }
+  } else if (warp < MMA_WARP && ROLE == ROLE_GATE) {
+    // ROLE_GATE ends in the LayerNorm role: no GEMM2, no role epilogue
   } else if (warp < MMA_WARP) {
     // =====================================================================================
     // E2: role epilogue on GEMM2's accumulator.  Two groups of four warps, thread = row (all 128 columns);
@@ -622,8 +651,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     const uint32_t a1_base = smem_u32(s_a1), ab_base = smem_u32(s_ab), w1r_base = smem_u32(s_w1r);
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int4 td_cur = nt > 0 ? __ldg(tiles) : zero4, td_n1 = nt > 1 ? __ldg(tiles + 1) : zero4;
-    load_ab(0, td_cur);
-    load_ab(1, td_n1);
+    if (ROLE != ROLE_GATE) { load_ab(0, td_cur); load_ab(1, td_n1); }
     int4 td_nx = nt > 2 ? __ldg(tiles + 2) : zero4;   // descriptor of tile t + 2, loaded one iteration early
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
@@ -634,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (R::SEP) { if (t >= ND1) mbar_wait(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
       else if (t >= ND1) mbar_wait(bar + B_E2_DONE + t % ND1, (t / ND1 - 1) & 1);             // tile t - ND1 left D[t % ND1]
       SMB_TRACE(12, t, lane == 0);
-      mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
+      if (ROLE != ROLE_GATE) mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(1, t, lane == 0);
       if (lane == 0) {
@@ -644,9 +672,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         const uint32_t sbo_ab = (uint32_t)(td_cur.z & 0xff) * 16u;   // n * 16: column-group stride of the projection tiles
         mma_ss(d, smem_desc(a1, 128, A1_SBO), smem_desc(w1r_base, 128, 512), IDESC1, 0);
         mma_ss(d, smem_desc(a1 + 256, 128, A1_SBO), smem_desc(w1r_base + 256, 128, 512), IDESC1, 1);
+        if (ROLE != ROLE_GATE) {
 #pragma unroll
-        for (int ks = 2; ks < K1 / 16; ++ks)
-          mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(ab + (ks >> 2) * (G * H * 2) + (ks & 1) * 256, 128, sbo_ab), IDESC1, 1);
+          for (int ks = 2; ks < K1 / 16; ++ks)
+            mma_ss(d, smem_desc(a1 + ks * 256, 128, A1_SBO), smem_desc(ab + (ks >> 2) * (G * H * 2) + (ks & 1) * 256, 128, sbo_ab), IDESC1, 1);
+        }
         SMB_TRACE(8, t, true);
         mma_commit(bar + B_A1_FREE + (t & 1));
         mma_commit(bar + B_D1_FULL + t % ND1);
@@ -654,9 +684,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       }
       __syncwarp();
       // projection slot (t + 2) % 3 was read by GEMM1(t - 1)
-      if (t >= 1) mbar_wait(bar + B_A1_FREE + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+      if (ROLE != ROLE_GATE && t >= 1) mbar_wait(bar + B_A1_FREE + ((t - 1) & 1), ((t - 1) >> 1) & 1);
       SMB_TRACE(10, t, lane == 0);
-      load_ab(t + 2, td_ld);
+      if (ROLE != ROLE_GATE) load_ab(t + 2, td_ld);
       SMB_TRACE(11, t, lane == 0);
       td_cur = td_n1; td_n1 = td_ld;
     }
@@ -667,7 +697,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     constexpr uint32_t IDESC2 = idesc_bf16(ROLE == ROLE_XV ? kHeads : H, false);
     const uint32_t w2_base = smem_u32(s_w2);
 #pragma unroll 1
-    for (int u = 0; u < nt; ++u) {
+    for (int u = 0; u < (ROLE == ROLE_GATE ? 0 : nt); ++u) {
       const int zb = u & 1;
       mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
       if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + u % ND2, (u / ND2 - 1) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
@@ -794,6 +824,7 @@ int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* 
 
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
   switch (role) {
+    case ROLE_GATE: return launch_ws<ROLE_GATE>(a, bn_rows_out, st);
     case ROLE_K: return launch_ws<ROLE_K>(a, bn_rows_out, st);
     case ROLE_V: return launch_ws<ROLE_V>(a, bn_rows_out, st);
     case ROLE_XV: return launch_ws<ROLE_XV>(a, bn_rows_out, st);

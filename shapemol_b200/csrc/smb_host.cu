@@ -49,9 +49,9 @@ EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
   e.b2 = c.take((gate ? 4 : n2) * 4);
   e.w1r_u = c.take((size_t)32 * H * 2);
   e.w2_u = gate ? e.w1r_u : c.take((size_t)n2 * H * 2);
-  e.w1r_f = gate ? e.w1r_u : c.take((size_t)32 * H * 2);
-  e.w2_f = gate ? e.w1r_u : c.take((size_t)n2 * H * 2);
-  e.beta_f = gate ? e.ln_b : c.take(H * 4);
+  e.w1r_f = c.take((size_t)32 * H * 2);
+  e.w2_f = gate ? c.take(H * 4) : c.take((size_t)n2 * H * 2);   // gate: fp32 vector w2 * |gamma|
+  e.beta_f = c.take(H * 4);
   return e;
 }
 NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2, bool folded = false, bool out_tc5 = false) {
@@ -278,6 +278,27 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
     if (gate) {
       put(blob, e.w2, w2, H);
       put(blob, e.b2, get(p + ".net.3.bias"), 1);
+      // warp-specialised pipeline: LayerNorm-folded first Linear with the (centred, signed) bias in k = 20 (hi) / 21 (lo)
+      const Fold fo = make_fold(p);
+      const float* b1 = get(p + ".net.0.bias");
+      uint16_t* f1 = reinterpret_cast<uint16_t*>(blob + e.w1r_f);
+      std::vector<float> col;
+      for (int k = 0; k < kRbf; ++k) {
+        folded_col(w1, ld1, k, fo, col);
+        for (int n = 0; n < H; ++n) f1[((size_t)(n / 8) * 512 + (size_t)k * 16 + (n % 8) * 2) / 2] = f2bf(col[n]);
+      }
+      double mb = 0.0;
+      for (int n = 0; n < H; ++n) mb += b1[n];
+      mb /= H;
+      for (int n = 0; n < H; ++n) {
+        const float b = fo.f[n] * (float)((double)b1[n] - mb);
+        const uint16_t hi = f2bf(b);
+        f1[((size_t)(n / 8) * 512 + (size_t)kRbf * 16 + (n % 8) * 2) / 2] = hi;
+        f1[((size_t)(n / 8) * 512 + (size_t)(kRbf + 1) * 16 + (n % 8) * 2) / 2] = f2bf(b - bf2f(hi));
+      }
+      float* wv = reinterpret_cast<float*>(blob + e.w2_f);
+      for (int n = 0; n < H; ++n) wv[n] = w2[n] * fo.mag[n];
+      put(blob, e.beta_f, fo.beta.data(), H);
     } else {
       pack_frags(blob + e.w2, n2 / 8, H / 16, prec, [&](int n, int k) { return w2[(size_t)n * H + k]; });
       put(blob, e.b2, get(p + ".net.3.bias"), n2);
