@@ -280,11 +280,16 @@ def main():
         hbm = peaks.get('hbm_gbs', 6650.0)
         if args.prof_kernel == 'edge_k':
             flops, fmin = E * F_REF_EDGE_K, E * F_MIN_EDGE_K
-            # reads: A,B projections (2*128*4 per atom), Q (512), x, nbr, e_w; writes alpha*e_w (64 B per edge)
-            bytes_alg = N * (2 * 512 + 512 + 12 + 2 * 4 * (args.k + 1)) + E * 64
+            # reads: A,B projections (bf16 images: 2*128*2 per atom; fp32 in the bf16x3 path), Q (512), x, nbr, e_w;
+            # writes alpha*e_w (64 B per edge)
+            proj = 2 * 256 if args.precision == 'bf16' else 2 * 512
+            bytes_alg = N * (proj + 512 + 12 + 2 * 4 * (args.k + 1)) + E * 64
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_v2_ncu_full_summary.txt);
+            # only valid for the default workload in bf16 mode
+            traffic = 240.0e6 if (args.precision == 'bf16' and args.shapes == 100 and args.per_shape == 50 and args.k == 32) else None
             roof = {'kernel': 'edge_kernel<ROLE_K> (edge MLP + attention logits + per-destination softmax)',
                     'bound': 'tensor', 'achieved': flops / (kms * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': flops / (kms * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                    'frac': flops / (kms * 1e-3) / 1e12 / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
                     'ms_per_launch': kms, 'launches_per_step': 16, 'share_of_step': 16 * kms / ms,
                     'flops_per_launch_ref': flops, 'flops_per_launch_factored': fmin,
                     'achieved_factored_tflops': fmin / (kms * 1e-3) / 1e12,
