@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SMB_ABI_VERSION 1
+#define SMB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SMB_API __attribute__((visibility("default")))
@@ -135,6 +135,11 @@ typedef struct smb_forward_io {
   int32_t prof_kernel;
   int32_t prof_capacity;
   void* const* prof_events;
+  /* != 0: the caller promises that `workspace` still holds the step-independent quantities of an earlier smb_forward call
+   * with the SAME batch, shape tensor and weights (invariant shape embedding, shape part of the VN maps, edge tile list);
+   * they are not recomputed.  The sampling loop sets it from its second step on (models/molopt_score_model.py:558-681 calls
+   * the network 1000 times with the same condition shape). */
+  int32_t reuse_static;
 } smb_forward_io;
 
 enum {

@@ -34,7 +34,8 @@ class ForwardIO(C.Structure):
                 ('bn_weight', _fp * SMB_MAX_LAYERS), ('bn_bias', _fp * SMB_MAX_LAYERS),
                 ('bn_running_mean', _fp * SMB_MAX_LAYERS), ('bn_running_var', _fp * SMB_MAX_LAYERS),
                 ('bn_num_batches_tracked', _fp * SMB_MAX_LAYERS), ('training', C.c_int32),
-                ('prof_kernel', C.c_int32), ('prof_capacity', C.c_int32), ('prof_events', C.POINTER(_fp))]
+                ('prof_kernel', C.c_int32), ('prof_capacity', C.c_int32), ('prof_events', C.POINTER(_fp)),
+                ('reuse_static', C.c_int32)]
 
 PROF = {'edge_k': 1, 'edge_v': 2, 'edge_xv': 3, 'node_pre': 4, 'node_out': 5, 'gate': 6, 'knn': 7, 'head': 8}
 
@@ -96,7 +97,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.smb_abi_version() != 1:
+    if lib.smb_abi_version() != 2:
         raise SmbError('ABI version mismatch')
     _lib = lib
     return lib

@@ -91,7 +91,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   pa.inv_bb = fptr(blob, L.inv_bb); pa.inv_w2 = fptr(blob, L.inv_w2); pa.inv_b2 = fptr(blob, L.inv_b2);
   pa.tau = tau; pa.inv = inv;
   float* vn_shape = wptr<float>(ws_base, W.vn_shape);
-  pa.n_layers = d.layers; pa.vn_shape = vn_shape;
+  pa.n_layers = d.layers; pa.vn_shape = vn_shape; pa.do_shape = io.reuse_static ? 0 : 1;
   for (int l = 0; l < d.layers; ++l) { pa.vn_w[l][0] = fptr(blob, L.layer[l].vn_feat); pa.vn_w[l][1] = fptr(blob, L.layer[l].vn_dir); }
   SMB_LAUNCH(launch_prep(pa, st));
 
@@ -108,7 +108,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   const bool node_tc5 = ws && node_tc5_supported(d, n_max);
   int4* tiles = wptr<int4>(ws_base, W.tiles + 16);
   int* n_tiles = wptr<int>(ws_base, W.tiles);
-  if (ws) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
+  if (ws && !io.reuse_static) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
   auto edge = [&](int role, const EdgeArgs& e, int* bn_rows) -> int {
     return ws ? launch_edge_ws(role, e, bn_rows, st) : launch_edge(d, role, e, bn_rows, st);
   };

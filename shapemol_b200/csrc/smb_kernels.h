@@ -20,6 +20,7 @@ struct PrepArgs {
   int n_layers;
   const float* vn_w[kMaxLayers][2];   // map_to_feat / map_to_dir weights [16][49]
   float* vn_shape;         // [L][B][96] or NULL
+  int do_shape;            // 0: only the time embedding (the shape-dependent outputs are still valid)
 };
 
 struct EmbedArgs {

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
     if (lane < 8) a.tau[m * 8 + lane] = out;
   }
   // ---- invariant shape embedding (lane = channel) ----
-  {
+  if (a.do_shape) {
     const float* s = a.shape + (size_t)m * kShape * 3 + lane * 3;
     const float sx = s[0], sy = s[1], sz = s[2];
     const float inv32 = 1.f / 32.f;

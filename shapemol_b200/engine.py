@@ -49,6 +49,7 @@ class DenoiseEngine:
         self._packed = None
         self._packed_key = None
         self._ws = None
+        self._static_key = None  # (batch, shape, workspace, weights) whose step-independent quantities the workspace holds
         self._names = None
 
     # ---- configuration ---------------------------------------------------------------------
@@ -98,7 +99,8 @@ class DenoiseEngine:
         return [blk.h2x_layers[0].shape_linear.batchnorm.bn for blk in self.module.refine_net.base_block]
 
     # ---- one network evaluation --------------------------------------------------------------
-    def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None, prof=None):
+    def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None, prof=None,
+                reuse_static=False):
         dims = self.dims()
         dev = pos.device
         blob = self.packed_weights(dev)
@@ -115,6 +117,12 @@ class DenoiseEngine:
             io.bn_running_mean[l], io.bn_running_var[l] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             io.bn_num_batches_tracked[l] = bn.num_batches_tracked.data_ptr()
         io.training = int(self.module.training if training is None else training)
+        # step-independent workspace contents (invariant shape embedding, VN shape maps, tile list) are kept only if the
+        # previous full evaluation used the same batch descriptor, shape tensor, workspace and packed weights
+        key = (id(bd), shape.data_ptr(), ws.data_ptr(), blob.data_ptr())
+        reuse = bool(reuse_static) and key == self._static_key
+        self._static_key = key
+        io.reuse_static = int(reuse)
         if prof is not None:      # (kernel class name, [torch.cuda.Event pairs, already created])
             cls, events = prof
             handles = (C.c_void_p * len(events))(*[ev.cuda_event for ev in events])
@@ -163,6 +171,9 @@ class Sampler:
     """Reverse-diffusion loop (ScorePosNet3D.sample_diffusion default branch) with persistent device
     state, no host synchronisation inside the loop and the step captured in a CUDA graph.
 
+    While a Sampler is running (and in particular while its captured graph is replayed) no other batch may be evaluated
+    through the same engine: from the second step on the step-independent workspace contents are reused.
+
     noise = 'torch'  : per step torch.randn_like(pos) then torch.rand(N, C) from the device's default
                        generator -- the reference's draw order, so torch.manual_seed(s) reproduces it;
             'philox' : in-kernel Philox4x32 keyed by (seed, global atom index, t)   (throughput mode);
@@ -202,7 +213,8 @@ class Sampler:
 
     def _step_body(self, step):
         e = self.e
-        e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v)
+        # from the second step on the step-independent quantities in the engine's workspace are still valid
+        e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v, reuse_static=step > 0)
         if self.noise == 'torch':
             self.noise_pos.normal_()     # == torch.randn_like(pos): same generator consumption
             self.noise_u.uniform_()      # == torch.rand_like(logits)

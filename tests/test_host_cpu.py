@@ -73,7 +73,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.smb_abi_version() == 1
+    assert lib.smb_abi_version() == 2
 
 
 def test_param_enumeration_and_packing_host_side():

@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel timing breakdown of one denoising step (bf16 mode): tools/bench_roles.sh [kernels...]
 for k in "${@:-edge_k edge_v edge_xv node_pre}"; do for kk in $k; do
-timeout 200 python bench.py --precision bf16 --steps 5 --warmup 3 --no-cpu-baseline --no-parity-mode --prof-kernel $kk > gpurun_out/b_ws_$kk.log 2>&1
+timeout 100 python bench.py --precision bf16 --steps 5 --warmup 3 --no-cpu-baseline --no-parity-mode --prof-kernel $kk > gpurun_out/b_ws_$kk.log 2>&1
 python - <<PY
 import json
 l=[x for x in open("gpurun_out/b_ws_$kk.log") if x.startswith("{")]
