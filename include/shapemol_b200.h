@@ -193,6 +193,35 @@ SMB_API int smb_debug_ws_trace(int64_t* host_out);
 
 SMB_API int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream);
 
+/* ---- point-cloud shape guidance ----------------------------------------------------
+ * Replaces pointcloud_shape_guidance (models/molopt_score_model.py:699-740; called at :582-591 on the predicted x0
+ * while t > grad_step): every atom whose mean distance to its 3 nearest cloud points exceeds `radius` is pulled
+ * towards their centroid by a random fraction in [ratio, 0.8), up to 5 times, until that mean distance is below
+ * `radius`.  The reference does this on the host (sklearn KDTree, numpy RNG, D2H + H2D per step); here it is one
+ * kernel, brute-force 3-NN in float64 in the reference's evaluation order (bit-exact against it for the same scalars).
+ *   pos        [N,3] fp32, in/out
+ *   cloud      [M,3] fp64 (utils/shape.py:164-173 produces float64), cloud_ptr NULL: every atom uses all M points;
+ *              else int32 [n_mols+1]: molecule m uses points cloud_ptr[m] .. cloud_ptr[m+1]-1 (needs batch->atom_mol)
+ *   t          NULL, or int32 [n_mols]: atoms of molecule m are only touched when t[m] > grad_step (device-side test,
+ *              so the call can sit inside a captured CUDA graph)
+ *   u          NULL: Philox4x32-10 keyed by (seed, atom_offset + atom, t or step, iteration); else fp64 [5][N] scalars
+ *              in [0,1) (parity tests; entry [j][i] is used iff atom i is still far in iteration j) */
+typedef struct smb_guidance_io {
+  float* pos;
+  const double* cloud;
+  const int32_t* cloud_ptr;
+  int32_t n_cloud;
+  const int32_t* t;
+  int32_t grad_step;
+  int32_t step;            /* Philox counter word when t == NULL */
+  double radius;
+  double ratio;            /* reference default 0.2 */
+  const double* u;
+  uint64_t seed;
+  int64_t atom_offset;
+} smb_guidance_io;
+SMB_API int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_io* io, void* stream);
+
 /* ---- VN-DGCNN shape encoder ---------------------------------------------------------------------
  * Replaces: VN_DGCNN_Encoder.forward (models/shape_pointcloud_modelAE.py:231-255).
  * clouds [B,P,3] fp32 -> latent [B,latent,3].  Weight pointers are DEVICE fp32 tensors taken from

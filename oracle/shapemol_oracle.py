@@ -426,3 +426,47 @@ DEFAULT_CFG = dict(num_blocks=1, num_layers=8, hidden_dim=128, n_heads=16, knn=3
 
 def mol_ptr_from_sizes(sizes):
     return torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.as_tensor(sizes, dtype=torch.long), 0)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Point-cloud shape guidance: models/molopt_score_model.py:699-740, applied to the predicted x0 while
+# t > grad_step (:582-591).  Every atom is independent.  The reference draws its pull-back scalars from numpy's global
+# RNG, one per atom that is still "far" in iteration j, in ascending atom order; here they are an explicit dense input
+# u[j][atom] (float64; entries of atoms that are not far in iteration j are never read).
+# Arithmetic follows the reference's numpy / sklearn float64 evaluation order exactly (KDTree.query = exact Euclidean
+# distances in double, sum over x, y, z in that order; np.mean over the 3 neighbours = ((a + b) + c) / 3).
+# ---------------------------------------------------------------------------------------------
+def _three_nn(points, cloud):
+    """points [n,3] f64, cloud [M,3] f64 -> (dists [n,3] ascending, idx [n,3]); ties broken by lower index."""
+    dx = points[:, None, 0] - cloud[None, :, 0]
+    dy = points[:, None, 1] - cloud[None, :, 1]
+    dz = points[:, None, 2] - cloud[None, :, 2]
+    d2 = (dx * dx + dy * dy) + dz * dz
+    order = torch.sort(d2, dim=1, stable=True)
+    return torch.sqrt(order.values[:, :3]), order.indices[:, :3]
+
+
+def pointcloud_guidance(pos, cloud, radius, u, ratio=0.2, max_iter=5):
+    """pos [N,3] f32 (predicted x0), cloud [M,3] f64, u [max_iter,N] f64 in [0,1) -> guided pos [N,3] f32."""
+    cloud = cloud.to(torch.float64)
+    p = pos.to(torch.float64).clone()
+    out = pos.clone()
+    span = 0.8 - ratio
+    dists, idx = _three_nn(p, cloud)
+    far = ((dists[:, 0] + dists[:, 1]) + dists[:, 2]) / 3.0 > radius
+    atoms = torch.nonzero(far).flatten()
+    pts, nn = p[atoms], idx[atoms]
+    j = 0
+    while atoms.numel() > 0 and j < max_iter:
+        c = cloud[nn]                                              # [n,3 neighbours,3]
+        near = ((c[:, 0] + c[:, 1]) + c[:, 2]) / 3.0
+        s = (u[j, atoms] * span + ratio)[:, None]
+        new = pts - s * (pts - near)
+        dists, idx = _three_nn(new, cloud)
+        inside = ((dists[:, 0] + dists[:, 1]) + dists[:, 2]) / 3.0 < radius
+        out[atoms[inside]] = new[inside].to(torch.float32)
+        atoms, pts, nn = atoms[~inside], new[~inside], idx[~inside]
+        j += 1
+    if j == max_iter and atoms.numel() > 0:
+        out[atoms] = pts.to(torch.float32)
+    return out

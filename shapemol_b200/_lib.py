@@ -49,6 +49,12 @@ class PosteriorIO(C.Structure):
                 ('log_one_minus_alphas_cumprod_v', _fp)]
 
 
+class GuidanceIO(C.Structure):
+    _fields_ = [('pos', _fp), ('cloud', _fp), ('cloud_ptr', _fp), ('n_cloud', C.c_int32), ('t', _fp), ('grad_step', C.c_int32),
+                ('step', C.c_int32), ('radius', C.c_double), ('ratio', C.c_double), ('u', _fp), ('seed', C.c_uint64),
+                ('atom_offset', C.c_int64)]
+
+
 class EncoderWeights(C.Structure):
     _fields_ = [('hidden', C.c_int32), ('latent', C.c_int32), ('n_blocks', C.c_int32), ('num_k', C.c_int32),
                 ('conv_pos_feat', _fp), ('conv_pos_dir', _fp), ('conv_pos_bn_w', _fp), ('conv_pos_bn_b', _fp),
@@ -72,6 +78,7 @@ EXPORTS = {
     'smb_type_head': (C.c_int, [C.POINTER(ModelDims), _fp, C.POINTER(Batch), _fp, _fp, _fp]),
     'smb_posterior_step': (C.c_int, [C.POINTER(ModelDims), C.POINTER(Batch), C.POINTER(PosteriorIO), _fp]),
     'smb_decrement_t': (C.c_int, [_fp, C.c_int32, _fp]),
+    'smb_pointcloud_guidance': (C.c_int, [C.POINTER(Batch), C.POINTER(GuidanceIO), _fp]),
     'smb_debug_ws_trace': (C.c_int, [_fp]),
     'smb_encoder_workspace_bytes': (C.c_size_t, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32]),
     'smb_vn_dgcnn_encode': (C.c_int, [C.POINTER(EncoderWeights), _fp, C.c_int32, C.c_int32, _fp, _fp, C.c_size_t, _fp]),

@@ -287,6 +287,18 @@ int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batch, const
   return rc;
 }
 
+int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_io* io, void* stream) {
+  if (!io) { smb::set_error_msg("smb_pointcloud_guidance: null argument"); return SMB_E_BADARG; }
+  int rc = smb::check_batch(batch);
+  if (rc) return rc;
+  if (batch->n_atoms == 0) return 0;
+  if (!io->pos || !io->cloud || io->n_cloud < 0) { smb::set_error_msg("smb_pointcloud_guidance: null pos / cloud"); return SMB_E_BADARG; }
+  if (!(io->radius > 0.0) || !(io->ratio >= 0.0 && io->ratio < 0.8)) { smb::set_error_msg("smb_pointcloud_guidance: radius must be > 0 and 0 <= ratio < 0.8"); return SMB_E_BADARG; }
+  rc = smb::launch_guidance(*io, batch->n_atoms, (io->cloud_ptr || io->t) ? batch->atom_mol : nullptr, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("guidance_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
 int smb_debug_ws_trace(int64_t* host_out) { return smb::debug_ws_trace(reinterpret_cast<long long*>(host_out)); }
 
 int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream) {

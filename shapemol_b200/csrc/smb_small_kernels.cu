@@ -361,6 +361,69 @@ int launch_posterior(const PosteriorArgs& a, cudaStream_t st) {
   posterior_kernel<<<(a.n_atoms + 127) / 128, 128, 0, st>>>(a);
   return (int)cudaGetLastError();
 }
+// -------------------------------------------------------------------------------------------
+// Point-cloud shape guidance: one thread per atom (models/molopt_score_model.py:699-740).  Float64 in the reference's
+// (numpy / sklearn) evaluation order, every operation individually rounded: no FMA contraction.
+// -------------------------------------------------------------------------------------------
+struct Nn3 { double d[3]; int i[3]; };
+
+__device__ __forceinline__ void three_nn(const double* __restrict__ cloud, int c0, int c1, double px, double py, double pz, Nn3& r) {
+  r.d[0] = r.d[1] = r.d[2] = INFINITY;
+  r.i[0] = r.i[1] = r.i[2] = c0;
+  for (int c = c0; c < c1; ++c) {
+    const double dx = __dsub_rn(px, cloud[3 * c]), dy = __dsub_rn(py, cloud[3 * c + 1]), dz = __dsub_rn(pz, cloud[3 * c + 2]);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (d2 < r.d[2]) {                       // strict: the lower index wins ties
+      if (d2 < r.d[1]) {
+        r.d[2] = r.d[1]; r.i[2] = r.i[1];
+        if (d2 < r.d[0]) { r.d[1] = r.d[0]; r.i[1] = r.i[0]; r.d[0] = d2; r.i[0] = c; }
+        else { r.d[1] = d2; r.i[1] = c; }
+      } else { r.d[2] = d2; r.i[2] = c; }
+    }
+  }
+}
+__device__ __forceinline__ double mean3(double a, double b, double c) { return __ddiv_rn(__dadd_rn(__dadd_rn(a, b), c), 3.0); }
+
+__global__ void __launch_bounds__(128) guidance_kernel(smb_guidance_io io, int n_atoms, const int* __restrict__ atom_mol) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_atoms) return;
+  const int m = atom_mol ? atom_mol[i] : 0;
+  int tt = io.step;
+  if (io.t) { tt = io.t[m]; if (tt <= io.grad_step) return; }
+  const int c0 = io.cloud_ptr ? io.cloud_ptr[m] : 0, c1 = io.cloud_ptr ? io.cloud_ptr[m + 1] : io.n_cloud;
+  if (c1 - c0 < 3) return;
+  double px = (double)io.pos[3 * i], py = (double)io.pos[3 * i + 1], pz = (double)io.pos[3 * i + 2];
+  Nn3 nn;
+  three_nn(io.cloud, c0, c1, px, py, pz, nn);
+  if (!(mean3(sqrt(nn.d[0]), sqrt(nn.d[1]), sqrt(nn.d[2])) > io.radius)) return;
+  const double span = __dsub_rn(0.8, io.ratio);
+  const uint64_t gi = (uint64_t)(io.atom_offset + i);
+  const uint2 key = make_uint2((uint32_t)io.seed, (uint32_t)(io.seed >> 32));
+  for (int j = 0; j < 5; ++j) {
+    double uj;
+    if (io.u) uj = io.u[(size_t)j * n_atoms + i];
+    else {   // 53 random bits -> [0, 1), as numpy's random_sample
+      const uint4 r = philox4x32(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)tt, 0x47554944u + (uint32_t)j), key);
+      uj = (double)(((uint64_t)(r.x >> 5) << 26) | (uint64_t)(r.y >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    const double* a = io.cloud + 3 * (size_t)nn.i[0];
+    const double* b = io.cloud + 3 * (size_t)nn.i[1];
+    const double* c = io.cloud + 3 * (size_t)nn.i[2];
+    const double s = __dadd_rn(__dmul_rn(uj, span), io.ratio);
+    px = __dsub_rn(px, __dmul_rn(s, __dsub_rn(px, mean3(a[0], b[0], c[0]))));
+    py = __dsub_rn(py, __dmul_rn(s, __dsub_rn(py, mean3(a[1], b[1], c[1]))));
+    pz = __dsub_rn(pz, __dmul_rn(s, __dsub_rn(pz, mean3(a[2], b[2], c[2]))));
+    three_nn(io.cloud, c0, c1, px, py, pz, nn);
+    if (mean3(sqrt(nn.d[0]), sqrt(nn.d[1]), sqrt(nn.d[2])) < io.radius) break;
+  }
+  io.pos[3 * i] = (float)px; io.pos[3 * i + 1] = (float)py; io.pos[3 * i + 2] = (float)pz;
+}
+
+int launch_guidance(const smb_guidance_io& io, int n_atoms, const int* atom_mol, cudaStream_t st) {
+  if (n_atoms <= 0) return 0;
+  guidance_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(io, n_atoms, atom_mol);
+  return (int)cudaGetLastError();
+}
 int launch_decrement_t(int* t, int n, cudaStream_t st) {
   if (n <= 0) return 0;
   decrement_t_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, n);

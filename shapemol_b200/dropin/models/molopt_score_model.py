@@ -204,20 +204,29 @@ class ScorePosNet3D(nn.Module):
                          threshold_args=None, num_steps=None, center_pos_mode=None, use_grad=False, grad_lr=1,
                          shape_AE=None, use_mesh_data=None, use_pointcloud_data=None, grad_step=500,
                          guide_stren=0, bounds=None):
-        """Reverse diffusion -- reference :533-697, default (no-guidance) branch."""
+        """Reverse diffusion -- reference :533-697: default branch and the point-cloud guidance branch ("ShapeMol+g")."""
         from shapemol_b200.engine import Sampler
         if num_steps is None:
             num_steps = self.num_timesteps
         print('sample center pos mode: ', center_pos_mode)
         if self.cond_mask_prob == 0:
             assert guide_stren == 0
-        if use_mesh_data is not None or use_pointcloud_data is not None or (self.cond_mask_prob > 0 and guide_stren > 0.0):
-            raise NotImplementedError('shape guidance / classifier-free guidance branches are not built (SURVEY 8f-1)')
+        if use_mesh_data is not None or (self.cond_mask_prob > 0 and guide_stren > 0.0):
+            raise NotImplementedError('mesh guidance / classifier-free guidance branches are not built (SURVEY 8f-1)')
+        guidance = None
+        if use_pointcloud_data is not None:
+            # (point_clouds [M,3] numpy float64, sklearn KDTree, radius) as scripts/sample_diffusion.py:237-241 builds it; the
+            # KD-tree is not used: the kernel does the 3-NN search itself (reference :582-591, :699-740)
+            import numpy as np
+            point_clouds, _, radius = use_pointcloud_data
+            cloud = torch.as_tensor(np.asarray(point_clouds, dtype=np.float64)).to(init_ligand_pos.device).contiguous()
+            guidance = dict(cloud=cloud, radius=float(radius), grad_step=int(grad_step), ratio=0.2)
         if center_pos_mode not in (None, 'none'):
             raise NotImplementedError("center_pos_mode=%r is not built (shipped configs use 'none')" % (center_pos_mode,))
         eng = self._engine()
         sampler = Sampler(eng, init_ligand_pos, init_ligand_v, batch_ligand, ligand_shape, num_steps=num_steps,
-                          noise=self.smb_noise, seed=self.smb_seed, keep_traj=self.smb_keep_traj, use_graph=self.smb_use_graph)
+                          noise=self.smb_noise, seed=self.smb_seed, keep_traj=self.smb_keep_traj, use_graph=self.smb_use_graph,
+                          guidance=guidance)
         pos, v = sampler.run(progress=lambda it: tqdm(it, desc='sampling', total=num_steps))
         out = {'pos': pos, 'v': v.to(torch.long), 'pos_traj': [], 'pos_cond_traj': [], 'pos_uncond_traj': [], 'v_traj': [],
                'v_cond_traj': [], 'v_uncond_traj': [], 'v0_traj': [], 'vt_traj': []}

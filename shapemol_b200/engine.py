@@ -155,6 +155,19 @@ class DenoiseEngine:
         stream = torch.cuda.current_stream(pos.device).cuda_stream
         _lib.check(self.lib.smb_posterior_step(C.byref(dims), C.byref(bd.c), C.byref(io), stream), 'smb_posterior_step')
 
+    # ---- point-cloud shape guidance on the predicted x0 (reference :582-591, :699-740) ----------------
+    def guidance(self, bd, pos, cloud_f64, radius, ratio=0.2, t_i32=None, grad_step=0, step=0, u=None, cloud_ptr=None, seed=0,
+                 atom_offset=0):
+        if cloud_f64.dtype != torch.float64 or cloud_f64.device != pos.device or not cloud_f64.is_contiguous():
+            raise _lib.SmbError('the condition point cloud must be a contiguous float64 [M,3] tensor on %s' % pos.device)
+        io = _lib.GuidanceIO()
+        io.pos, io.cloud, io.cloud_ptr, io.n_cloud = pos.data_ptr(), cloud_f64.data_ptr(), _lib.ptr(cloud_ptr), int(cloud_f64.shape[0])
+        io.t, io.grad_step, io.step = _lib.ptr(t_i32), int(grad_step), int(step)
+        io.radius, io.ratio, io.u = float(radius), float(ratio), _lib.ptr(u)
+        io.seed, io.atom_offset = int(seed) & (2 ** 64 - 1), int(atom_offset)
+        stream = torch.cuda.current_stream(pos.device).cuda_stream
+        _lib.check(self.lib.smb_pointcloud_guidance(C.byref(bd.c), C.byref(io), stream), 'smb_pointcloud_guidance')
+
     def decrement_t(self, t_i32):
         stream = torch.cuda.current_stream(t_i32.device).cuda_stream
         _lib.check(self.lib.smb_decrement_t(t_i32.data_ptr(), t_i32.numel(), stream), 'smb_decrement_t')
@@ -181,7 +194,7 @@ class Sampler:
     """
 
     def __init__(self, engine, init_pos, init_v, batch_ligand, shape, num_steps=None, noise='torch', seed=0, atom_offset=0,
-                 keep_traj=True, use_graph=True, n_mols=None):
+                 keep_traj=True, use_graph=True, n_mols=None, guidance=None):
         m = engine.module
         self.e = engine
         dev = init_pos.device
@@ -205,6 +218,9 @@ class Sampler:
         self.log_post = torch.empty(N, Cn, device=dev) if keep_traj else None
         self.use_graph = use_graph and not callable(noise)
         self.graph = None
+        # guidance: dict(cloud=[M,3] float64 device tensor, radius=..., grad_step=..., ratio=0.2, cloud_ptr=None): point-cloud
+        # shape guidance of the predicted x0 while t > grad_step ("ShapeMol+g"); the kernel tests t on the device
+        self.guidance = guidance
         if keep_traj:
             S = self.num_steps
             self.traj = {k: torch.empty((S,) + tuple(s), dtype=dt, device=dev) for k, s, dt in (
@@ -215,6 +231,10 @@ class Sampler:
         e = self.e
         # from the second step on the step-independent quantities in the engine's workspace are still valid
         e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v, reuse_static=step > 0)
+        if self.guidance is not None:
+            gd = self.guidance
+            e.guidance(self.bd, self.pred_pos, gd['cloud'], gd['radius'], ratio=gd.get('ratio', 0.2), t_i32=self.t,
+                       grad_step=gd['grad_step'], cloud_ptr=gd.get('cloud_ptr'), seed=self.seed, atom_offset=self.atom_offset)
         if self.noise == 'torch':
             self.noise_pos.normal_()     # == torch.randn_like(pos): same generator consumption
             self.noise_u.uniform_()      # == torch.rand_like(logits)

@@ -1,5 +1,6 @@
 """Pins the oracle (oracle/shapemol_oracle.py) against fixtures produced by the UNMODIFIED
 reference modules (tests/golden/make_golden.py).  CPU only."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -78,3 +79,17 @@ def test_encoder_matches_reference(name, mode):
     with torch.no_grad():
         lat = orc.encoder_forward(w, fx['%s_clouds' % name], k=fx['num_k'], training=(mode == 'train'))
     assert torch.allclose(lat, fx['%s_%s_latent' % (name, mode)], rtol=1e-4, atol=1e-5)
+
+
+def test_pointcloud_guidance_oracle_matches_reference_bit_for_bit():
+    """tests/golden/guidance.pt: outputs of the unmodified pointcloud_shape_guidance (models/molopt_score_model.py:699-740)
+    with sklearn's KDTree and recorded numpy draws (make_guidance_golden.py)."""
+    cases = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'guidance.pt'))
+    assert len(cases) == 4
+    for c in cases:
+        got = orc.pointcloud_guidance(c['pos'], c['cloud'], c['radius'], torch.nan_to_num(c['u'], nan=0.5))
+        assert torch.equal(got, c['out'])
+        # atoms that start within the radius are never touched; moved atoms end closer to the cloud's 3-NN centroid
+        d, _ = orc._three_nn(c['pos'].double(), c['cloud'])
+        near = d.mean(1) <= c['radius']
+        assert torch.equal(got[near], c['pos'][near])
