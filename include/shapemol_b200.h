@@ -222,6 +222,16 @@ typedef struct smb_guidance_io {
 } smb_guidance_io;
 SMB_API int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_io* io, void* stream);
 
+/* ---- alignment-free shape Tanimoto ---------------------------------------------------
+ * Replaces get_ROCS (utils/evaluation/shaep_utils.py:59-83) for a whole batch: molecule m's generated centres
+ * pos[mol_ptr[m] .. mol_ptr[m+1]) against the reference centres ref[ref_ptr[m] .. ref_ptr[m+1]) (fp64 [R,3]);
+ * ref_ptr NULL: every molecule is compared with all n_ref reference centres.
+ *   out[m] = V_AB / (V_AA + V_BB - V_AB),  V_XY = sum_ij coef * exp(-k |x_i - y_j|^2) / den
+ * (k, coef, den): the reference's float32 per-atom constants for prefactor 0.8 / alpha 0.81, see
+ * oracle rocs_constants(); float64 accumulation in a fixed order (deterministic). */
+SMB_API int smb_shape_tanimoto(const smb_batch* batch, const float* pos, const double* ref, const int32_t* ref_ptr, int32_t n_ref,
+                       double k, double coef, double den, double* out, void* stream);
+
 /* ---- VN-DGCNN shape encoder ---------------------------------------------------------------------
  * Replaces: VN_DGCNN_Encoder.forward (models/shape_pointcloud_modelAE.py:231-255).
  * clouds [B,P,3] fp32 -> latent [B,latent,3].  Weight pointers are DEVICE fp32 tensors taken from

@@ -470,3 +470,37 @@ def pointcloud_guidance(pos, cloud, radius, u, ratio=0.2, max_iter=5):
     if j == max_iter and atoms.numel() > 0:
         out[atoms] = pts.to(torch.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Alignment-free Gaussian-overlap shape Tanimoto: utils/evaluation/shaep_utils.py:59-83 (get_ROCS, all
+# atoms alpha = 0.81, prefactor 0.8).  Float64, explicit pair distances.
+# ---------------------------------------------------------------------------------------------
+def rocs_constants(prefactor=0.8, alpha=0.81):
+    """The reference builds its per-atom constants with torch.ones(...) * x, i.e. in float32, and only the pair distances
+    are float64: (k, coef, den) with  term = coef * exp(-k R^2) / den  (shaep_utils.py:59-66)."""
+    a, p = np.float32(alpha), np.float32(prefactor)
+    k = np.float32(np.float32(a * a) / np.float32(a + a))
+    coef = np.float32(np.float32(math.pi ** 1.5) * np.float32(p * p))
+    den = np.float32(np.float32(a + a) ** np.float32(1.5))
+    return float(k), float(coef), float(den)
+
+
+def _vab(c1, c2, consts):
+    k, coef, den = consts
+    d = c1[:, None, :] - c2[None, :, :]
+    r2 = torch.sqrt((d * d).sum(-1)) ** 2.0          # the reference squares torch.cdist
+    return (coef * torch.exp(-k * r2) / den).sum()
+
+
+def get_rocs(centers_1, centers_2, prefactor=0.8, alpha=0.81):
+    c1, c2 = centers_1.to(torch.float64), centers_2.to(torch.float64)
+    cs = rocs_constants(prefactor, alpha)
+    vaa, vbb, vab = _vab(c1, c1, cs), _vab(c2, c2, cs), _vab(c1, c2, cs)
+    return vab / (vaa + vbb - vab)
+
+
+def get_rocs_batch(pos, mol_ptr, ref, ref_ptr):
+    """Per-molecule Tanimoto of generated centres pos[mol_ptr[m]:mol_ptr[m+1]] against ref[ref_ptr[m]:ref_ptr[m+1]]."""
+    return torch.stack([get_rocs(pos[int(mol_ptr[m]):int(mol_ptr[m + 1])], ref[int(ref_ptr[m]):int(ref_ptr[m + 1])])
+                        for m in range(len(mol_ptr) - 1)])

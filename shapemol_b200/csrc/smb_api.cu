@@ -299,6 +299,17 @@ int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_io* io, v
   return rc;
 }
 
+int smb_shape_tanimoto(const smb_batch* batch, const float* pos, const double* ref, const int32_t* ref_ptr, int32_t n_ref, double k,
+                       double coef, double den, double* out, void* stream) {
+  int rc = smb::check_batch(batch);
+  if (rc) return rc;
+  if (batch->n_mols == 0) return 0;
+  if (!pos || !ref || !out || (!ref_ptr && n_ref <= 0)) { smb::set_error_msg("smb_shape_tanimoto: null pointer / empty reference"); return SMB_E_BADARG; }
+  rc = smb::launch_tanimoto(pos, batch->mol_ptr, batch->n_mols, ref, ref_ptr, n_ref, k, coef, den, out, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("tanimoto_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
 int smb_debug_ws_trace(int64_t* host_out) { return smb::debug_ws_trace(reinterpret_cast<long long*>(host_out)); }
 
 int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream) {

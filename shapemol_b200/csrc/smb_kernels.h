@@ -146,6 +146,8 @@ int launch_bn_final(const BnArgs& a, cudaStream_t st);
 int launch_vn_apply(const float* vn, const float* bn_param, float* x, float* x_out, int n_atoms, cudaStream_t st);
 int launch_posterior(const PosteriorArgs& a, cudaStream_t st);
 int launch_decrement_t(int* t, int n, cudaStream_t st);
+int launch_tanimoto(const float* pos, const int* mol_ptr, int n_mols, const double* ref, const int* ref_ptr, int n_ref, double k,
+                    double coef, double den, double* out, cudaStream_t st);
 int launch_guidance(const smb_guidance_io& io, int n_atoms, const int* atom_mol, cudaStream_t st);
 
 }  // namespace smb

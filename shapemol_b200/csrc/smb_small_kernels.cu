@@ -424,6 +424,47 @@ int launch_guidance(const smb_guidance_io& io, int n_atoms, const int* atom_mol,
   guidance_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(io, n_atoms, atom_mol);
   return (int)cudaGetLastError();
 }
+// -------------------------------------------------------------------------------------------
+// Shape Tanimoto of get_ROCS (utils/evaluation/shaep_utils.py:59-83): one warp per molecule, float64.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double overlap_sum(const double* a, int na, const double* b, int nb, double k, double coef, double den, int lane) {
+  double acc = 0.0;
+  for (int p = lane; p < na * nb; p += 32) {
+    const int i = p / nb, j = p - i * nb;
+    const double dx = a[3 * i] - b[3 * j], dy = a[3 * i + 1] - b[3 * j + 1], dz = a[3 * i + 2] - b[3 * j + 2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    acc += coef * exp(-k * (r * r)) / den;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__global__ void __launch_bounds__(128) tanimoto_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr, int n_mols,
+                                                       const double* __restrict__ ref, const int* __restrict__ ref_ptr, int n_ref, double k,
+                                                       double coef, double den, double* __restrict__ out) {
+  __shared__ double s_a[4][SMB_MAX_ATOMS_PER_MOL * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= n_mols) return;
+  const int a0 = mol_ptr[m], na = mol_ptr[m + 1] - a0;
+  const int r0 = ref_ptr ? ref_ptr[m] : 0, nr = ref_ptr ? ref_ptr[m + 1] - r0 : n_ref;
+  for (int p = lane; p < na * 3; p += 32) s_a[warp][p] = (double)pos[(size_t)a0 * 3 + p];
+  __syncwarp();
+  const double* b = ref + (size_t)r0 * 3;
+  const double vaa = overlap_sum(s_a[warp], na, s_a[warp], na, k, coef, den, lane);
+  const double vbb = overlap_sum(b, nr, b, nr, k, coef, den, lane);
+  const double vab = overlap_sum(s_a[warp], na, b, nr, k, coef, den, lane);
+  if (lane == 0) out[m] = vab / (vaa + vbb - vab);
+}
+
+int launch_tanimoto(const float* pos, const int* mol_ptr, int n_mols, const double* ref, const int* ref_ptr, int n_ref, double k,
+                    double coef, double den, double* out, cudaStream_t st) {
+  if (n_mols <= 0) return 0;
+  tanimoto_kernel<<<(n_mols + 3) / 4, 128, 0, st>>>(pos, mol_ptr, n_mols, ref, ref_ptr, n_ref, k, coef, den, out);
+  return (int)cudaGetLastError();
+}
+
 int launch_decrement_t(int* t, int n, cudaStream_t st) {
   if (n <= 0) return 0;
   decrement_t_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, n);

@@ -168,6 +168,23 @@ class DenoiseEngine:
         stream = torch.cuda.current_stream(pos.device).cuda_stream
         _lib.check(self.lib.smb_pointcloud_guidance(C.byref(bd.c), C.byref(io), stream), 'smb_pointcloud_guidance')
 
+    # ---- alignment-free shape Tanimoto of every molecule against its reference centres (get_ROCS) ------
+    def shape_tanimoto(self, bd, pos, ref_f64, ref_ptr=None, prefactor=0.8, alpha=0.81):
+        import math
+        import numpy as np
+        if ref_f64.dtype != torch.float64 or ref_f64.device != pos.device or not ref_f64.is_contiguous():
+            raise _lib.SmbError('reference centres must be a contiguous float64 [R,3] tensor on %s' % pos.device)
+        # the reference's per-atom constants are float32 (torch.ones(n) * x, utils/evaluation/shaep_utils.py:76-79)
+        a, p = np.float32(alpha), np.float32(prefactor)
+        k = float(np.float32(np.float32(a * a) / np.float32(a + a)))
+        coef = float(np.float32(np.float32(math.pi ** 1.5) * np.float32(p * p)))
+        den = float(np.float32(np.float32(a + a) ** np.float32(1.5)))
+        out = torch.empty(bd.n_mols, dtype=torch.float64, device=pos.device)
+        stream = torch.cuda.current_stream(pos.device).cuda_stream
+        _lib.check(self.lib.smb_shape_tanimoto(C.byref(bd.c), pos.data_ptr(), ref_f64.data_ptr(), _lib.ptr(ref_ptr), int(ref_f64.shape[0]),
+                                               k, coef, den, out.data_ptr(), stream), 'smb_shape_tanimoto')
+        return out
+
     def decrement_t(self, t_i32):
         stream = torch.cuda.current_stream(t_i32.device).cuda_stream
         _lib.check(self.lib.smb_decrement_t(t_i32.data_ptr(), t_i32.numel(), stream), 'smb_decrement_t')

@@ -93,3 +93,11 @@ def test_pointcloud_guidance_oracle_matches_reference_bit_for_bit():
         d, _ = orc._three_nn(c['pos'].double(), c['cloud'])
         near = d.mean(1) <= c['radius']
         assert torch.equal(got[near], c['pos'][near])
+
+
+def test_shape_tanimoto_oracle_matches_reference():
+    """tests/golden/rocs.pt: outputs of the unmodified get_ROCS (utils/evaluation/shaep_utils.py:59-83)."""
+    cases = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'rocs.pt'))
+    for c in cases:
+        assert abs(float(orc.get_rocs(c['a'], c['b'])) - float(c['rocs'])) < 1e-12
+    assert abs(float(orc.get_rocs(cases[-1]['a'], cases[-1]['b'])) - 1.0) < 1e-12      # identical centre sets
