@@ -44,8 +44,15 @@ constexpr int A1_BYTES = TM * K1 * 2;  // 24576
 constexpr int AB_BYTES = 2 * G * H * 2;  // 16384: A-tile | B-tile, each [32 k][128 n] MN-major
 constexpr int LS = 17;                 // padded row stride of per-row head scratch
 constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
-constexpr int P_WARPS = 2, GRP_WARPS = 8, WARPS = 20, THREADS = WARPS * 32;   // 20 warps -> 96 registers per thread
-constexpr int LN_WARP0 = P_WARPS, E2_WARP0 = LN_WARP0 + GRP_WARPS, MMA_WARP = E2_WARP0 + GRP_WARPS;
+// 28 warps = 7 warpgroups, launched at 72 registers per thread and re-balanced per role with setmaxnreg (Regs<ROLE>):
+//   WG0     warps  0-3   P (2 warps, two rows per thread), GEMM1 issuer + loader, GEMM2 issuer     72 (unchanged)
+//   WG1-2   warps  4-11  LN                                                                           88 / 96
+//   WG3-6   warps 12-27  E2: ROLE_XV four groups at 64; ROLE_K / ROLE_V two groups at 96, the rest idle at 24
+constexpr int P_WARPS = 2, GRP_WARPS = 8, NG_MAX = 4, WARPS = 28, THREADS = WARPS * 32;
+constexpr int MMA_WARP = 2, G2_WARP = 3, LN_WARP0 = 4, E2_WARP0 = LN_WARP0 + GRP_WARPS;
+constexpr int REGS_IDLE = 24;
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
 constexpr int BAR_LN = 1, BAR_E2 = 2;   // named barriers (0 is __syncthreads); E2 group g uses BAR_E2 + g
 constexpr int E2_GRP_THREADS = 128;
 constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
@@ -53,13 +60,22 @@ constexpr int GRP_THREADS = GRP_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
 
 // mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14, B_E2_DONE = 22, B_AB_FULL = 30, B_D1_FREE = 33, N_BARS = 35 };
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14, B_E2_DONE = 26, B_AB_FULL = 38, B_D1_FREE = 41, N_BARS = 43 };
 // TMEM accumulator rings (512 columns in all):
 //   ROLE_K : 3 x 128 (GEMM2 overwrites GEMM1's accumulator in place) + z[2] x 64
 //   ROLE_V : 4 x 128 in place; z lives in shared memory
 //   ROLE_XV: GEMM2 has 16 output columns, so it gets its own ring: D1 2 x 128 | z[2] x 64 | D2 8 x 16.  D1 is free again as
 //            soon as the LayerNorm has read it, and a late epilogue no longer stalls GEMM1.
 template <int ROLE> struct Ring {
+  // epilogue groups: ROLE_V's shared memory (z^T operands) has room for two staging areas only
+  static constexpr int NG = ROLE == ROLE_GATE ? 0 : ROLE == ROLE_XV ? 4 : 2;
+  // register budgets (pool: 7 warpgroups x 72 = 504):  72 + 2 LN + NG E2 + (4 - NG) 24 <= 504
+  static constexpr int REGS_LN = ROLE == ROLE_XV ? 88 : 96, REGS_E2 = ROLE == ROLE_XV ? 64 : 96;
+  static_assert(72 + 2 * REGS_LN + NG * REGS_E2 + (4 - NG) * REGS_IDLE <= 504, "register pool");
+  // D2_FULL / E2_DONE mbarriers are indexed by tile % NB2 (the TMEM buffer by tile % ND2).  A parity wait is only
+  // unambiguous if the waiter visits every phase of its barrier: an epilogue group sees tiles g, g + NG, ..., so NB2 must
+  // be a multiple of both NG and ND2 (ROLE_K: 3 buffers, 4 groups -> 12 barriers)
+  static constexpr int NB2 = ROLE == ROLE_K ? 6 : (ROLE == ROLE_XV || ROLE == ROLE_GATE) ? 8 : 4;
   static constexpr bool SEP = ROLE == ROLE_XV || ROLE == ROLE_GATE;   // ROLE_GATE has no GEMM2 at all
   static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 3;
   static constexpr int ND2 = SEP ? 8 : ND1;
@@ -69,8 +85,8 @@ template <int ROLE> struct Ring {
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 35 mbarriers
-  static constexpr int o_tmem = 288;
+  static constexpr int o_bar = 0;                 // 43 mbarriers
+  static constexpr int o_tmem = 352;
   static constexpr int o_vec = 384;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
   static constexpr int o_w2 = o_w1r + 8192;
@@ -83,14 +99,16 @@ struct Plan {
   // E2 scratch, one per group: two staging slots (ROLE_K: q float[16][128]; ROLE_V: alpha float[128][16];
   // ROLE_XV: alpha | shape float[96]), then role scratch
   static constexpr int stage_bytes = ROLE == ROLE_XV ? 8192 + 384 : 8192;
-  static constexpr int n_slots = ROLE == ROLE_V ? 1 : 2;   // ROLE_V (z^T operands in smem) has room for one
+  // ROLE_K stages q one tile of the group ahead (two slots); the others stage after the group's previous tile
+  static constexpr int n_slots = ROLE == ROLE_K ? 2 : 1;
   static constexpr int e_stage = 0;
   static constexpr int e_log = n_slots * stage_bytes;       // ROLE_K logits / ROLE_XV w : float[128][17]
   static constexpr int e_red = e_log + 8704;          // ROLE_K float2[16][16]
   static constexpr int e_rel = e_log + 8704;          // ROLE_XV float4[128]
   static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[16][16][4]
   static constexpr int e2_bytes = ROLE == ROLE_K ? e_red + 2048 : ROLE == ROLE_V ? n_slots * stage_bytes : e_o + 4096;
-  static constexpr int o_vnw = o_e2 + 2 * e2_bytes;       // ROLE_XV: vn_feat | vn_dir
+  static constexpr int NGP = ROLE == ROLE_XV ? 4 : 2;
+  static constexpr int o_vnw = o_e2 + NGP * e2_bytes;     // ROLE_XV: vn_feat | vn_dir
   static constexpr int total = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);
   static_assert(total <= 227 * 1024, "shared memory budget");
   static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0 && e2_bytes % 16 == 0, "alignment");
@@ -152,7 +170,8 @@ template <int ROLE>
 __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
   using P = Plan<ROLE>;
   using R = Ring<ROLE>;
-  constexpr int ND1 = R::ND1, ND2 = R::ND2;
+  constexpr int ND1 = R::ND1, ND2 = R::ND2, NB2 = R::NB2;
+  static_assert(NB2 % ND2 == 0 && (R::NG == 0 || NB2 % R::NG == 0) && NB2 <= 12, "barrier ring");
   constexpr uint32_t Z_COL = R::Z_COL;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::o_bar);
@@ -203,8 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       mbar_init(bar + B_A1_FREE + b, 1);
       mbar_init(bar + B_Z_FULL + b, GRP_THREADS);
     }
-    for (int b = 0; b < 8; ++b) {
-      mbar_init(bar + B_D1_FULL + b, 1);
+    for (int b = 0; b < 8; ++b) mbar_init(bar + B_D1_FULL + b, 1);
+    for (int b = 0; b < 12; ++b) {
       mbar_init(bar + B_D2_FULL + b, 1);
       mbar_init(bar + B_E2_DONE + b, E2_GRP_THREADS);
     }
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
+  // every role branch starts with its warpgroups' register re-balancing (setmaxnreg is warpgroup-aligned)
   if (warp < P_WARPS) {
     // =====================================================================================
     // P: A1 operand.  Row r of the tile is edge (i <- j): i = d0 + r / deg, slot s = r % deg.
@@ -306,7 +326,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(0, t, tid == 0);
       mbar_arrive(bar + B_A1_FULL + slot);
     }
-  } else if (warp < E2_WARP0) {
+  } else if (warp >= LN_WARP0 && warp < E2_WARP0) {
+    reg_inc<R::REGS_LN>();
     // =====================================================================================
     // LN: D -> LayerNorm -> ReLU -> z (bf16).  thread = (row, column half); every tile.
     // =====================================================================================
@@ -358,7 +379,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         continue;
       }
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
-      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % ND2, ((t - 2) / ND2) & 1);
+      if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % NB2, ((t - 2) / NB2) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
       if (!(a.dbg & 2))
 #pragma unroll
@@ -381,18 +402,18 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(3, t, gw == 0 && lane == 0);
       mbar_arrive(bar + B_Z_FULL + zb);
     }
-  } else if (warp < MMA_WARP && ROLE == ROLE_GATE) {
-    // ROLE_GATE ends in the LayerNorm role: no GEMM2, no role epilogue
-  } else if (warp < MMA_WARP) {
-    // =====================================================================================
-    // E2: role epilogue on GEMM2's accumulator.  Two groups of four warps, thread = row (all 128 columns);
-    // group g owns tiles g, g + 2, ... so that two tiles' epilogues (and their barriers) overlap.
-    // =====================================================================================
+  } else if (warp >= E2_WARP0 && (ROLE == ROLE_GATE || ((warp - E2_WARP0) >> 2) >= R::NG)) {
+    // ROLE_GATE ends in the LayerNorm role: no GEMM2, no role epilogue; ROLE_V uses two of the four groups.
+    // Idle warpgroups give their registers back.
+    reg_dec<REGS_IDLE>();
+  } else if (warp >= E2_WARP0) {
+    if (R::REGS_E2 > 72) reg_inc<R::REGS_E2>(); else reg_dec<R::REGS_E2>();
     const int e2w = warp - E2_WARP0;
     const int g = e2w >> 2, qd = warp & 3;
     const int r = qd * 32 + lane;            // TMEM lane = tile row (ROLE_V: output channel)
     const int tg = (e2w & 3) * 32 + lane;    // thread index inside the group
     const int bar_id = BAR_E2 + g;
+    constexpr int NG = R::NG > 0 ? R::NG : 1;
     const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
     unsigned char* es = smem + P::o_e2 + g * P::e2_bytes;
     float* s_log = reinterpret_cast<float*>(es + P::e_log);             // ROLE_K logits, ROLE_XV w
@@ -435,20 +456,20 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int4 td_cur = g < nt ? __ldg(tiles + g) : zero4;
-    int4 td_nx = g + 2 < nt ? __ldg(tiles + g + 2) : zero4;
+    int4 td_nx = g + NG < nt ? __ldg(tiles + g + NG) : zero4;
     if (g < nt) stage(g, Tile(td_cur));
     cp_async_commit();
 #pragma unroll 1
-    for (int t = g; t < nt; t += 2) {
+    for (int t = g; t < nt; t += NG) {
       const Tile T(td_cur);
       const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
       td_cur = td_nx;
-      if (t + 4 < nt) td_nx = __ldg(tiles + t + 4);
+      if (t + 2 * NG < nt) td_nx = __ldg(tiles + t + 2 * NG);
       if (P::n_slots == 2) {
-        if (t + 2 < nt) stage(t + 2, Tile(td_cur));   // the other slot: its readers (tile t - 2) are behind the trailing barrier
+        if (t + NG < nt) stage(t + NG, Tile(td_cur));   // the other slot: its readers are behind the trailing barrier
         cp_async_commit();
       }
-      const int b3 = t % ND2;
+      const int b3 = t % ND2, bb = t % NB2;   // TMEM buffer / barrier slot
       const uint32_t dcol = R::D2_COL + (uint32_t)b3 * R::D2_STRIDE;
       const int rows = T.rows();
       const bool valid = r < rows;
@@ -460,11 +481,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
       if (P::n_slots == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
-      mbar_wait(bar + B_D2_FULL + b3, (t / ND2) & 1);
+      mbar_wait(bar + B_D2_FULL + bb, (t / NB2) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
       named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
-      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); named_sync(bar_id, E2_GRP_THREADS); continue; }
+      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); named_sync(bar_id, E2_GRP_THREADS); continue; }
 
       if (ROLE == ROLE_K) {
         float l[16];
@@ -476,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           tmem_ld32(lane_addr + dcol + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           tmem_ld32(lane_addr + dcol + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           wait_ld();
-          if (hf == 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + b3); }
+          if (hf == 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); }
           const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + hf * 64);
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
@@ -576,14 +597,14 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           }
         }
         fence_before_sync();
-        mbar_arrive(bar + B_E2_DONE + b3);
+        mbar_arrive(bar + B_E2_DONE + bb);
       } else {   // ROLE_XV
         {
           uint32_t v[16];
           tmem_ld16(lane_addr + dcol, v);
           wait_ld();
           fence_before_sync();
-          mbar_arrive(bar + B_E2_DONE + b3);
+          mbar_arrive(bar + B_E2_DONE + bb);
           if (valid) {
             const float4* al = reinterpret_cast<const float4*>(s_al + r * kHeads);
 #pragma unroll
@@ -646,13 +667,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(6, t, tg == 0);
       named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slots are reused by the group's next tiles
       if (P::n_slots == 1) {
-        if (t + 2 < nt) stage(t + 2, Tile(td_cur));
+        if (t + NG < nt) stage(t + NG, Tile(td_cur));
         cp_async_commit();
       }
     }   // tiles
     cp_async_wait<0>();
     if (ROLE == ROLE_XV && lane < 16) {
-      float* part = a.bn_partial + (size_t)(blockIdx.x * GRP_WARPS + e2w) * 32;
+      float* part = a.bn_partial + (size_t)(blockIdx.x * (4 * NG_MAX) + e2w) * 32;
       part[lane] = bn_s;
       part[16 + lane] = bn_q;
     }
@@ -688,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
       SMB_TRACE(7, t, lane == 0);
       if (R::SEP) { if (t >= ND1) mbar_wait(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
-      else if (t >= ND1) mbar_wait(bar + B_E2_DONE + t % ND1, (t / ND1 - 1) & 1);             // tile t - ND1 left D[t % ND1]
+      else if (t >= ND1) mbar_wait(bar + B_E2_DONE + (t - ND1) % NB2, ((t - ND1) / NB2) & 1);   // tile t - ND1 left D[t % ND1]
       SMB_TRACE(12, t, lane == 0);
       if (ROLE != ROLE_GATE) mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
@@ -718,7 +739,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(11, t, lane == 0);
       td_cur = td_n1; td_n1 = td_ld;
     }
-  } else {
+  } else if (warp == G2_WARP) {
     // =====================================================================================
     // GEMM2 issuer
     // =====================================================================================
@@ -728,7 +749,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     for (int u = 0; u < (ROLE == ROLE_GATE ? 0 : nt); ++u) {
       const int zb = u & 1;
       mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
-      if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + u % ND2, (u / ND2 - 1) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
+      if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + (u - ND2) % NB2, ((u - ND2) / NB2) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
       fence_after_sync();
       SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {
@@ -743,7 +764,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           for (int ks = 0; ks < H / 16; ++ks)
             mma_ts(d, tmem + Z_COL + zb * 64 + ks * 8, smem_desc(w2_base + ks * 256, 128, 2048), IDESC2, ks > 0);
         }
-        mma_commit(bar + B_D2_FULL + u % ND2);
+        mma_commit(bar + B_D2_FULL + u % NB2);
       }
       __syncwarp();
     }
@@ -829,7 +850,7 @@ int launch_ws(const EdgeArgs& a_in, int* bn_rows_out, cudaStream_t st) {
   }
   int grid = sms();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
-  if (bn_rows_out) *bn_rows_out = grid * GRP_WARPS;
+  if (bn_rows_out) *bn_rows_out = grid * (4 * NG_MAX);
   edge_ws_kernel<ROLE><<<grid, THREADS, Plan<ROLE>::total, st>>>(a);
   return (int)cudaGetLastError();
 }
