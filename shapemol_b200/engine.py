@@ -298,8 +298,9 @@ class HostStepper:
     """One denoising step with HOST buffers on both sides (the end-to-end call bench.py times):
     pinned host (x_t, v_t, t, shape) -> H2D -> network + posterior -> D2H (x_{t-1}, v_{t-1})."""
 
-    def __init__(self, engine, batch_ligand_dev, n_mols, noise='philox', seed=0):
+    def __init__(self, engine, batch_ligand_dev, n_mols, noise='philox', seed=0, use_graph=True):
         m = engine.module
+        self.use_graph, self._graph, self._graph_key = use_graph, None, None
         self.e = engine
         self.bd = BatchDesc(batch_ligand_dev, n_mols)
         dev = batch_ligand_dev.device
@@ -317,9 +318,7 @@ class HostStepper:
         self.h2d_bytes = N * 12 + N * 4 + B * 4 + B * 32 * 3 * 4
         self.d2h_bytes = N * 12 + N * 4
 
-    def step(self, h_pos, h_v, h_t, h_shape):
-        """h_*: pinned host tensors.  Returns pinned host (pos_next, v_next); asynchronous on the
-        current stream (synchronise before reading)."""
+    def _enqueue(self, h_pos, h_v, h_t, h_shape):
         self.d_pos.copy_(h_pos, non_blocking=True)
         self.d_v.copy_(h_v, non_blocking=True)
         self.d_t.copy_(h_t, non_blocking=True)
@@ -328,4 +327,21 @@ class HostStepper:
         self.e.posterior(self.bd, self.pred_pos, self.pred_v, self.d_t, self.d_pos, self.d_v, seed=self.seed)
         self.h_pos_out.copy_(self.d_pos, non_blocking=True)
         self.h_v_out.copy_(self.d_v, non_blocking=True)
+
+    def step(self, h_pos, h_v, h_t, h_shape):
+        """h_*: pinned host tensors.  Returns pinned host (pos_next, v_next); asynchronous on the
+        current stream (synchronise before reading).  The whole step -- the four H2D copies, every kernel and the two D2H
+        copies -- is captured once per set of host buffers in a CUDA graph and replayed."""
+        key = (h_pos.data_ptr(), h_v.data_ptr(), h_t.data_ptr(), h_shape.data_ptr())
+        if self.use_graph and all(t.is_pinned() for t in (h_pos, h_v, h_t, h_shape)):
+            if self._graph_key != key:
+                self._enqueue(h_pos, h_v, h_t, h_shape)          # eager once: warms up and validates before capture
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(h_pos, h_v, h_t, h_shape)
+                self._graph, self._graph_key = g, key
+            self._graph.replay()
+        else:
+            self._enqueue(h_pos, h_v, h_t, h_shape)
         return self.h_pos_out, self.h_v_out

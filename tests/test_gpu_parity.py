@@ -309,3 +309,26 @@ def test_train_mode_bn_couples_batch_like_reference(cuda_lib):
     m.eval()
     out_eval = m(pos.cuda(), v.cuda(), batch_of(sizes), shape.cuda(), time_step=t.cuda())
     assert rel_err(out_eval['pred_ligand_pos'], ex) > 1e-3
+
+
+def test_host_stepper_graph_equals_eager(cuda_lib):
+    """The end-to-end host-buffer step bench.py times (H2D copies + network + posterior + D2H copies), captured in a
+    CUDA graph, returns exactly what the eager enqueue returns."""
+    from shapemol_b200.engine import HostStepper
+    fx = load_golden('forward_k32_eval.pt')
+    sizes = fx['sizes']
+    batch = batch_of(sizes)
+    N, B = sum(sizes), len(sizes)
+    h_pos, h_v = fx['pos'].clone().pin_memory(), fx['v'].to(torch.int32).pin_memory()
+    h_t, h_shape = torch.full((B,), 500, dtype=torch.int32).pin_memory(), fx['shape'].clone().pin_memory()
+    outs = []
+    for use_graph in (False, True):
+        m = build_model(fx, 'bf16', training=False)
+        hs = HostStepper(m._engine(), batch, B, seed=9, use_graph=use_graph)
+        for _ in range(3):                       # replays must be idempotent for fixed host inputs
+            p, v = hs.step(h_pos, h_v, h_t, h_shape)
+        torch.cuda.synchronize()
+        outs.append((p.clone(), v.clone()))
+        assert p.shape == (N, 3) and bool(torch.isfinite(p).all())
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.equal(outs[0][0], fx['pos'])

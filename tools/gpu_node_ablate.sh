@@ -1,5 +1,5 @@
 #!/bin/bash
-for d in 0 1 2 4 3 7; do for k in node_pre node_out; do
+for d in ${DBGS:-0 7 15 23 31}; do for k in node_pre; do
 SMB_NODE_DBG=$d timeout 200 python bench.py --precision bf16 --steps 3 --warmup 3 --no-cpu-baseline --no-parity-mode --prof-kernel $k > /tmp/ab.log 2>&1
 python - <<PY
 import json
