@@ -109,7 +109,8 @@ struct Plan {
   static constexpr int e2_bytes = ROLE == ROLE_K ? e_red + 2048 : ROLE == ROLE_V ? n_slots * stage_bytes : e_o + 4096;
   static constexpr int NGP = ROLE == ROLE_XV ? 4 : 2;
   static constexpr int o_vnw = o_e2 + NGP * e2_bytes;     // ROLE_XV: vn_feat | vn_dir
-  static constexpr int total = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);
+  static constexpr int o_bn = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);   // ROLE_XV: float[16 E2 warps][32] BatchNorm partial sums
+  static constexpr int total = o_bn + (ROLE == ROLE_XV ? 4 * NG_MAX * 32 * 4 : 0);
   static_assert(total <= 227 * 1024, "shared memory budget");
   static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0 && e2_bytes % 16 == 0, "alignment");
 };
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     }   // tiles
     cp_async_wait<0>();
     if (ROLE == ROLE_XV && lane < 16) {
-      float* part = a.bn_partial + (size_t)(blockIdx.x * (4 * NG_MAX) + e2w) * 32;
+      float* part = reinterpret_cast<float*>(smem + P::o_bn) + e2w * 32;   // summed per CTA after the final barrier
       part[lane] = bn_s;
       part[16 + lane] = bn_q;
     }
@@ -772,6 +773,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
   fence_before_sync();
   __syncthreads();
+  if (ROLE == ROLE_XV && warp == 1) {   // one BatchNorm partial row per CTA, fixed summation order (deterministic)
+    const float* part = reinterpret_cast<const float*>(smem + P::o_bn);
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4 * R::NG; ++w) acc += part[w * 32 + lane];
+    a.bn_partial[(size_t)blockIdx.x * 32 + lane] = acc;
+  }
   if (warp == 0) tmem_free<TMEM_COLS>(tmem);
 }
 
@@ -850,7 +858,7 @@ int launch_ws(const EdgeArgs& a_in, int* bn_rows_out, cudaStream_t st) {
   }
   int grid = sms();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
-  if (bn_rows_out) *bn_rows_out = grid * (4 * NG_MAX);
+  if (bn_rows_out) *bn_rows_out = grid;
   edge_ws_kernel<ROLE><<<grid, THREADS, Plan<ROLE>::total, st>>>(a);
   return (int)cudaGetLastError();
 }
