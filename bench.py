@@ -46,7 +46,7 @@ def ref_like_config(k=32):
         cond_mask_prob=0.0)
 
 
-def make_workload(n_shapes, per_shape, seed):
+def make_workload(n_shapes, per_shape, seed, fixed_atoms=0):
     """Synthetic MOSES-shaped batch: ragged atom counts from the size prior, N(0,1) initial positions,
     uniform initial types, N(0, 0.07^2) shape latents (one per shape, repeated per molecule)."""
     with open(os.path.join(ROOT, 'data', 'moses_atom_count_hist.json')) as f:
@@ -56,6 +56,8 @@ def make_workload(n_shapes, per_shape, seed):
     g = torch.Generator().manual_seed(seed)
     B = n_shapes * per_shape
     sizes = ns[torch.multinomial(w, B, replacement=True, generator=g)]
+    if fixed_atoms > 0:      # BASELINE configs[2]: every molecule has exactly this many atoms
+        sizes = torch.full((B,), int(fixed_atoms), dtype=torch.long)
     N = int(sizes.sum())
     batch = torch.repeat_interleave(torch.arange(B), sizes)
     pos = torch.randn(N, 3, generator=g)
@@ -142,6 +144,7 @@ def main():
     ap.add_argument('--shapes', type=int, default=100)
     ap.add_argument('--per-shape', type=int, default=50)
     ap.add_argument('--k', type=int, default=32)
+    ap.add_argument('--fixed-atoms', type=int, default=0, help='all molecules of this size (configs[2]: 27) instead of the MOSES size prior')
     ap.add_argument('--cpu-mols', type=int, default=50)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--prof-kernel', default='edge_k')
@@ -150,8 +153,8 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
-    workload = '%d shapes x %d molecules, MOSES size prior (9..27 atoms), k=%d, hidden 128, 8 layers, T=1000, train-mode BN' % (
-        args.shapes, args.per_shape, args.k)
+    workload = '%d shapes x %d molecules, %s, k=%d, hidden 128, 8 layers, T=1000, train-mode BN' % (
+        args.shapes, args.per_shape, ('%d atoms each' % args.fixed_atoms) if args.fixed_atoms else 'MOSES size prior (9..27 atoms)', args.k)
 
     if args.impl == 'reference':
         if rank != 0:
@@ -178,7 +181,7 @@ def main():
     from shapemol_b200.engine import Sampler, HostStepper
 
     model = build_model(args.k, args.precision).to(dev).train()
-    sizes, batch, pos, v, shape = make_workload(args.shapes, args.per_shape, 2021 + rank)
+    sizes, batch, pos, v, shape = make_workload(args.shapes, args.per_shape, 2021 + rank, args.fixed_atoms)
     B, N = sizes.numel(), int(sizes.sum())
     E = int((sizes * torch.clamp(sizes - 1, max=args.k)).sum())
     eng = model._engine()
@@ -286,7 +289,7 @@ def main():
             bytes_alg = N * (proj + 512 + 12 + 2 * 4 * (args.k + 1)) + E * 64
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_v2_ncu_full_summary.txt);
             # only valid for the default workload in bf16 mode
-            traffic = 240.0e6 if (args.precision == 'bf16' and args.shapes == 100 and args.per_shape == 50 and args.k == 32) else None
+            traffic = 240.0e6 if (args.precision == 'bf16' and args.shapes == 100 and args.per_shape == 50 and args.k == 32 and not args.fixed_atoms) else None
             roof = {'kernel': 'edge_kernel<ROLE_K> (edge MLP + attention logits + per-destination softmax)',
                     'bound': 'tensor', 'achieved': flops / (kms * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
                     'frac': flops / (kms * 1e-3) / 1e12 / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
