@@ -431,9 +431,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const int dl = min(T.dst_of(r), NDMAX - 1), sl = r - dl * T.deg;
       const bool valid = r < T.rows();
       if (ROLE == ROLE_K) {
-        const float* src = a.q + (size_t)(T.a0 + T.d0) * H;
+        // q arrives in node_tc5_kernel's tile image [128-row block][32 column groups][128 rows][4 floats]
         float* dst = reinterpret_cast<float*>(slot);
-        for (int p = tg; p < T.nd * (H / 4); p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        // consecutive threads fetch consecutive destinations of one column group: contiguous nd x 16 bytes in the image
+        for (int p = tg; p < T.nd * (H / 4); p += E2_GRP_THREADS) {
+          const int cg = p / T.nd, d = p - cg * T.nd, row = T.a0 + T.d0 + d;
+          cp_async16(dst + (d * 32 + cg) * 4, a.q + (size_t)(row >> 7) * (TM * H) + (size_t)cg * (TM * 4) + (row & 127) * 4);
+        }
         pre_ew = 0.f;
         if (valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
       } else {

@@ -134,7 +134,7 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.h_a = c.take(n * H * 4);
   w.h_b = c.take(n * H * 4);
   w.ab = c.take(n * 4 * H * 4);
-  w.q = c.take(n * H * 4);
+  w.q = c.take(align_up(n, 128) * H * 4);   // whole 128-row blocks (tile image of the tcgen05 node kernel)
   w.agg = c.take(n * H * 4);
   w.vn = c.take(n * kVnRow * 4);
   w.bn_part_rows = kEdgeMaxCtas * kEdgeWarps;

@@ -58,6 +58,8 @@ struct NodeMlpOff {
   size_t w2_t;   // [128 n][128 k] K-major (as EdgeMlpOff::w2_u), k-columns multiplied by |gamma|
   size_t beta_t; // [H] beta / |gamma|
 };
+// q of the tcgen05 node kernel (bf16 mode): tile image, float offset of (row r, column c) =
+//   (r / 128) * 128 * 128 + (c / 4) * 128 * 4 + (r % 128) * 4 + c % 4     (the workspace slot is sized for whole 128-row blocks)
 constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
 constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
 constexpr int kNodeOutKx = 272;                         // node_output: 128 (agg) + 128 (h) + 16 (bias hi | bias lo | zeros)

@@ -269,13 +269,18 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
           mbar_arrive(bar + B_Z_FULL);
         } else if (s == G2_STEP) {
           if (valid && !(a.dbg & 2)) {
-            float4* dst = reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
+            // MODE 0: q goes out in the tile image [128-row block][32 column groups][128 rows][4 floats] (kQImage in smb_layout.h): a
+            // warp's 32 rows store 512 contiguous bytes per column group instead of 32 scattered 16-byte pieces; the K edge role
+            // gathers its destinations' rows from it with 16-byte cp.async pieces.  MODE 1: h' stays row-major [N][128].
+            float4* dst = MODE == 0 ? reinterpret_cast<float4*>(a.out2 + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
+                                    : reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
+            constexpr int DSTEP = MODE == 0 ? TM : 1;   // float4 stride between consecutive column groups
             const float4* res = MODE == 1 ? reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64) : nullptr;
 #pragma unroll
             for (int e = 0; e < 64; e += 4) {
               float4 bb = *reinterpret_cast<const float4*>(s_b2 + half * 64 + e);
               if (MODE == 1) { const float4 rv = __ldg(res + e / 4); bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w; }
-              dst[e / 4] = make_float4(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y, __uint_as_float(v[e + 2]) + bb.z,
+              dst[(e / 4) * DSTEP] = make_float4(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y, __uint_as_float(v[e + 2]) + bb.z,
                                        __uint_as_float(v[e + 3]) + bb.w);
             }
           }
