@@ -140,6 +140,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_in; n.xb = inv; n.out1 = ab; n.out2 = q;
+      n.xa_image = node_tc5 && l > 0;
       fill_node_weights(n, blob, y.x2h_pre);
       if (ws) {   // bf16 operand images and LayerNorm-folded projections for the warp-specialised edge pipeline
         n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;
@@ -163,6 +164,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_AGG_H; n.act = ACT_LN_RELU; n.n_pass = 0; n.n2 = H; n.n2_valid = H;
       n.xa = agg; n.xb = h_in; n.residual = h_in; n.out2 = h_out;
+      n.xb_image = node_tc5 && l > 0; n.out2_image = node_tc5 && !last;
       fill_node_weights(n, blob, y.node_out);
       SMB_TIMED(SMB_PROF_NODE_OUT, node_tc5 ? launch_node_out_tc5(n, st) : launch_node_mlp(d, n, st));
     }
@@ -171,6 +173,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       NodeArgs n = na;
       n.x_mode = XMODE_H_INV; n.act = ACT_LN_RELU; n.n_pass = 4 * H; n.n2 = H; n.n2_valid = H;
       n.xa = h_out; n.xb = inv; n.out1 = ab; n.out2 = q;
+      n.xa_image = node_tc5 && !last;
       fill_node_weights(n, blob, y.h2x_pre);
       if (ws) {   // bf16 operand images and LayerNorm-folded projections for the warp-specialised edge pipeline
         n.out1_h = reinterpret_cast<uint32_t*>(ab); n.mol_ptr = b.mol_ptr;

@@ -131,8 +131,8 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
     w.alpha = c.take(by_atom > by_tile ? by_atom : by_tile);
   }
   w.x = c.take(n * 3 * 4);
-  w.h_a = c.take(n * H * 4);
-  w.h_b = c.take(n * H * 4);
+  w.h_a = c.take(align_up(n, 128) * H * 4);   // whole 128-row blocks: intermediate layers keep h as a tile image (bf16 mode)
+  w.h_b = c.take(align_up(n, 128) * H * 4);
   w.ab = c.take(n * 4 * H * 4);
   w.q = c.take(align_up(n, 128) * H * 4);   // whole 128-row blocks (tile image of the tcgen05 node kernel)
   w.agg = c.take(n * H * 4);

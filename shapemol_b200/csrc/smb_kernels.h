@@ -85,6 +85,10 @@ struct NodeArgs {
   const int* mol_ptr;
   float* out2;             // [N][n2_valid]
   const void *w1_t, *w2_t; const float* beta_t;   // tcgen05 operand images (NodeMlpOff::w1_t / w2_t / beta_t)
+  // tcgen05 node kernels: activations in the tile image [128-row block][32 column groups][128 rows][4 floats] instead of
+  // row-major [N][128] (warp-coalesced for thread-per-row accesses).  xa_image: XMODE_H_INV input h; xb_image: XMODE_AGG_H
+  // input h (= residual); out2_image: XMODE_AGG_H output h' (XMODE_H_INV always writes q as an image)
+  int xa_image, xb_image, out2_image;
   int dbg;                 // SMB_NODE_DBG bit mask (timing experiments only: results are wrong when set)
 };
 int launch_node_mlp(const smb_model_dims& d, const NodeArgs& a, cudaStream_t st);

@@ -192,16 +192,25 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
           const int rb = rp * RPB + q;
           const int grow = tile * TM + xw * 32 + rb * 8 + rr;
           if (mol[rb] >= 0 && !(a.dbg & 4)) {
-            const float4* hp = reinterpret_cast<const float4*>(a.xa + (size_t)grow * H + kq * 8);
+            // row-major [N][128] or tile image [block][32 column groups][128 rows][4] (NodeArgs::xa_image): eight consecutive
+            // columns are two float4 pieces `pst` apart; the next 32 columns are 8 pieces further
+            const int rt = grow - tile * TM;
+            const bool ia = MODE == 0 && a.xa_image;
+            const float4* hp = reinterpret_cast<const float4*>(ia ? a.xa + (size_t)tile * (TM * H) + (size_t)(kq * 2) * (TM * 4) + rt * 4
+                                                                  : a.xa + (size_t)grow * H + kq * 8);
+            const int pst = ia ? TM : 1;
 #pragma unroll
-            for (int st = 0; st < 4; ++st) { v[q][st][0] = __ldg(hp + st * 8); v[q][st][1] = __ldg(hp + st * 8 + 1); }
+            for (int st = 0; st < 4; ++st) { v[q][st][0] = __ldg(hp + st * 8 * pst); v[q][st][1] = __ldg(hp + (st * 8 + 1) * pst); }
             if (MODE == 0) {
               const float4* ip = reinterpret_cast<const float4*>(a.xb + (size_t)mol[rb] * kShape + kq * 8);
               v[q][4][0] = __ldg(ip); v[q][4][1] = __ldg(ip + 1);
             } else {
-              const float4* h2 = reinterpret_cast<const float4*>(a.xb + (size_t)grow * H + kq * 8);
+              const bool ib = a.xb_image != 0;
+              const float4* h2 = reinterpret_cast<const float4*>(ib ? a.xb + (size_t)tile * (TM * H) + (size_t)(kq * 2) * (TM * 4) + rt * 4
+                                                                    : a.xb + (size_t)grow * H + kq * 8);
+              const int pst2 = ib ? TM : 1;
 #pragma unroll
-              for (int st = 0; st < 4; ++st) { v[q][4 + st][0] = __ldg(h2 + st * 8); v[q][4 + st][1] = __ldg(h2 + st * 8 + 1); }
+              for (int st = 0; st < 4; ++st) { v[q][4 + st][0] = __ldg(h2 + st * 8 * pst2); v[q][4 + st][1] = __ldg(h2 + (st * 8 + 1) * pst2); }
             }
           } else {
 #pragma unroll
@@ -272,14 +281,19 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
             // MODE 0: q goes out in the tile image [128-row block][32 column groups][128 rows][4 floats] (kQImage in smb_layout.h): a
             // warp's 32 rows store 512 contiguous bytes per column group instead of 32 scattered 16-byte pieces; the K edge role
             // gathers its destinations' rows from it with 16-byte cp.async pieces.  MODE 1: h' stays row-major [N][128].
-            float4* dst = MODE == 0 ? reinterpret_cast<float4*>(a.out2 + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
-                                    : reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
-            constexpr int DSTEP = MODE == 0 ? TM : 1;   // float4 stride between consecutive column groups
-            const float4* res = MODE == 1 ? reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64) : nullptr;
+            const bool oi = MODE == 0 || a.out2_image;
+            float4* dst = oi ? reinterpret_cast<float4*>(a.out2 + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
+                             : reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
+            const int DSTEP = oi ? TM : 1;   // float4 stride between consecutive column groups
+            const bool ri = MODE == 1 && a.xb_image;   // the residual is the h operand (same layout)
+            const float4* res = MODE != 1 ? nullptr
+                                : ri ? reinterpret_cast<const float4*>(a.residual + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
+                                     : reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64);
+            const int RSTEP = ri ? TM : 1;
 #pragma unroll
             for (int e = 0; e < 64; e += 4) {
               float4 bb = *reinterpret_cast<const float4*>(s_b2 + half * 64 + e);
-              if (MODE == 1) { const float4 rv = __ldg(res + e / 4); bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w; }
+              if (MODE == 1) { const float4 rv = __ldg(res + (e / 4) * RSTEP); bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w; }
               dst[(e / 4) * DSTEP] = make_float4(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y, __uint_as_float(v[e + 2]) + bb.z,
                                        __uint_as_float(v[e + 3]) + bb.w);
             }
