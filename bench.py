@@ -287,7 +287,7 @@ def main():
             # writes alpha*e_w (64 B per edge)
             proj = 2 * 256 if args.precision == 'bf16' else 2 * 512
             bytes_alg = N * (proj + 512 + 12 + 2 * 4 * (args.k + 1)) + E * 64
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_v2_ncu_full_summary.txt);
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_v4_ncu_full_summary.txt);
             # only valid for the default workload in bf16 mode
             traffic = 240.0e6 if (args.precision == 'bf16' and args.shapes == 100 and args.per_shape == 50 and args.k == 32 and not args.fixed_atoms) else None
             roof = {'kernel': 'edge_kernel<ROLE_K> (edge MLP + attention logits + per-destination softmax)',
