@@ -229,6 +229,15 @@ SMB_API int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_i
  *   out[m] = V_AB / (V_AA + V_BB - V_AB),  V_XY = sum_ij coef * exp(-k |x_i - y_j|^2) / den
  * (k, coef, den): the reference's float32 per-atom constants for prefactor 0.8 / alpha 0.81, see
  * oracle rocs_constants(); float64 accumulation in a fixed order (deterministic). */
+/* ---- stability check -----------------------------------------------------------------
+ * Replaces check_stability / get_bond_order (utils/evaluation/analyze.py:249-297) for a whole batch: bond order of every
+ * atom pair of a molecule from its distance (float32, x100 = pm) against thr[k][e_i][e_j] = bond length + margin, k = single /
+ * double / triple; an atom is stable iff allowed[e] >= sum of its bond orders > 0 (hs != 0: ==).
+ *   elem   int32 [N] element index 0..n_elem-1;  thr int32 [3][n_elem][n_elem];  allowed int32 [n_elem]   (device pointers)
+ *   nr_bonds int32 [N] out (may be NULL);  stable_atoms int32 [n_mols] out;  a molecule is stable iff stable_atoms[m] == n_m */
+SMB_API int smb_check_stability(const smb_batch* batch, const float* pos, const int32_t* elem, const int32_t* thr, const int32_t* allowed,
+                        int32_t n_elem, int32_t hs, int32_t* nr_bonds, int32_t* stable_atoms, void* stream);
+
 SMB_API int smb_shape_tanimoto(const smb_batch* batch, const float* pos, const double* ref, const int32_t* ref_ptr, int32_t n_ref,
                        double k, double coef, double den, double* out, void* stream);
 

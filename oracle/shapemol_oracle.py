@@ -504,3 +504,27 @@ def get_rocs_batch(pos, mol_ptr, ref, ref_ptr):
     """Per-molecule Tanimoto of generated centres pos[mol_ptr[m]:mol_ptr[m+1]] against ref[ref_ptr[m]:ref_ptr[m+1]]."""
     return torch.stack([get_rocs(pos[int(mol_ptr[m]):int(mol_ptr[m + 1])], ref[int(ref_ptr[m]):int(ref_ptr[m + 1])])
                         for m in range(len(mol_ptr) - 1)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Stability check (SURVEY 8f-4): utils/evaluation/analyze.py:249-297 (get_bond_order, check_stability).  Table driven: thr
+# [3,E,E] int (bond length + margin in pm, shapemol_b200/chem_tables.py), allowed [E].  Distances in the positions' dtype
+# (float32 from the sampler), every operation individually rounded, then x 100 -- numpy >= 2 scalar promotion keeps float32.
+# ---------------------------------------------------------------------------------------------
+def check_stability(positions, elem, thr, allowed, hs=False):
+    """positions [n,3] f32, elem [n] element index -> (molecule_stable, nr_stable_atoms, n, nr_bonds [n])."""
+    p = positions.to(torch.float32)
+    n = p.shape[0]
+    dx, dy, dz = p[:, None, 0] - p[None, :, 0], p[:, None, 1] - p[None, :, 1], p[:, None, 2] - p[None, :, 2]
+    d = torch.sqrt((dx * dx + dy * dy) + dz * dz) * 100.0
+    e = elem.long()
+    t1, t2, t3 = (thr[k][e[:, None], e[None, :]].to(torch.float32) for k in range(3))
+    o1 = d < t1
+    o2 = o1 & (d < t2)
+    o3 = o2 & (d < t3)
+    order = o1.long() + o2.long() + o3.long()
+    order.fill_diagonal_(0)
+    nr = order.sum(1)
+    al = allowed[e].long()
+    ok = (al == nr) if hs else ((al >= nr) & (nr > 0))
+    return bool(ok.all()) if n else True, int(ok.sum()), n, nr

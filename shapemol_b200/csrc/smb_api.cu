@@ -302,6 +302,17 @@ int smb_pointcloud_guidance(const smb_batch* batch, const smb_guidance_io* io, v
   return rc;
 }
 
+int smb_check_stability(const smb_batch* batch, const float* pos, const int32_t* elem, const int32_t* thr, const int32_t* allowed,
+                        int32_t n_elem, int32_t hs, int32_t* nr_bonds, int32_t* stable_atoms, void* stream) {
+  int rc = smb::check_batch(batch);
+  if (rc) return rc;
+  if (batch->n_mols == 0) return 0;
+  if (!pos || !elem || !thr || !allowed || !stable_atoms || n_elem <= 0) { smb::set_error_msg("smb_check_stability: null pointer / empty tables"); return SMB_E_BADARG; }
+  rc = smb::launch_stability(pos, batch->mol_ptr, batch->n_mols, elem, thr, allowed, n_elem, hs, nr_bonds, stable_atoms, (cudaStream_t)stream);
+  if (rc > 0) smb::set_error("stability_kernel launch", (cudaError_t)rc);
+  return rc;
+}
+
 int smb_shape_tanimoto(const smb_batch* batch, const float* pos, const double* ref, const int32_t* ref_ptr, int32_t n_ref, double k,
                        double coef, double den, double* out, void* stream) {
   int rc = smb::check_batch(batch);

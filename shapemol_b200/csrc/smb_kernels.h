@@ -152,6 +152,8 @@ int launch_posterior(const PosteriorArgs& a, cudaStream_t st);
 int launch_decrement_t(int* t, int n, cudaStream_t st);
 int launch_tanimoto(const float* pos, const int* mol_ptr, int n_mols, const double* ref, const int* ref_ptr, int n_ref, double k,
                     double coef, double den, double* out, cudaStream_t st);
+int launch_stability(const float* pos, const int* mol_ptr, int n_mols, const int* elem, const int* thr, const int* allowed, int n_elem,
+                     int hs, int* nr_bonds, int* stable_atoms, cudaStream_t st);
 int launch_guidance(const smb_guidance_io& io, int n_atoms, const int* atom_mol, cudaStream_t st);
 
 }  // namespace smb

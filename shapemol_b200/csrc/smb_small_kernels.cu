@@ -465,6 +465,54 @@ int launch_tanimoto(const float* pos, const int* mol_ptr, int n_mols, const doub
   return (int)cudaGetLastError();
 }
 
+// -------------------------------------------------------------------------------------------
+// check_stability / get_bond_order (utils/evaluation/analyze.py:249-297): one warp per molecule, lane = atom (two per lane
+// for molecules of more than 32 atoms).  float32 distances in numpy's evaluation order, every operation individually rounded.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stability_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr, int n_mols,
+                                                        const int* __restrict__ elem, const int* __restrict__ thr,
+                                                        const int* __restrict__ allowed, int n_elem, int hs, int* __restrict__ nr_bonds,
+                                                        int* __restrict__ stable_atoms) {
+  __shared__ float s_x[4][SMB_MAX_ATOMS_PER_MOL][3];
+  __shared__ int s_e[4][SMB_MAX_ATOMS_PER_MOL];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= n_mols) return;
+  const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
+  for (int i = lane; i < n; i += 32) {
+    s_x[warp][i][0] = pos[(size_t)(a0 + i) * 3]; s_x[warp][i][1] = pos[(size_t)(a0 + i) * 3 + 1]; s_x[warp][i][2] = pos[(size_t)(a0 + i) * 3 + 2];
+    s_e[warp][i] = elem[a0 + i];
+  }
+  __syncwarp();
+  const int ee = n_elem * n_elem;
+  int stable = 0;
+  for (int i = lane; i < n; i += 32) {
+    const float xi = s_x[warp][i][0], yi = s_x[warp][i][1], zi = s_x[warp][i][2];
+    const int ei = s_e[warp][i];
+    int nb = 0;
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      const float dx = __fsub_rn(xi, s_x[warp][j][0]), dy = __fsub_rn(yi, s_x[warp][j][1]), dz = __fsub_rn(zi, s_x[warp][j][2]);
+      const float d = __fmul_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 100.f);
+      const int* t = thr + ei * n_elem + s_e[warp][j];
+      if (d < (float)t[0]) { nb += 1; if (d < (float)t[ee]) { nb += 1; if (d < (float)t[2 * ee]) nb += 1; } }
+    }
+    if (nr_bonds) nr_bonds[a0 + i] = nb;
+    const int al = allowed[ei];
+    stable += hs ? (al == nb) : (al >= nb && nb > 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) stable += __shfl_xor_sync(0xffffffffu, stable, o);
+  if (lane == 0) stable_atoms[m] = stable;
+}
+
+int launch_stability(const float* pos, const int* mol_ptr, int n_mols, const int* elem, const int* thr, const int* allowed, int n_elem,
+                     int hs, int* nr_bonds, int* stable_atoms, cudaStream_t st) {
+  if (n_mols <= 0) return 0;
+  stability_kernel<<<(n_mols + 3) / 4, 128, 0, st>>>(pos, mol_ptr, n_mols, elem, thr, allowed, n_elem, hs, nr_bonds, stable_atoms);
+  return (int)cudaGetLastError();
+}
+
 int launch_decrement_t(int* t, int n, cudaStream_t st) {
   if (n <= 0) return 0;
   decrement_t_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, n);

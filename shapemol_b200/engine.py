@@ -185,6 +185,22 @@ class DenoiseEngine:
                                                k, coef, den, out.data_ptr(), stream), 'smb_shape_tanimoto')
         return out
 
+    # ---- stability check of every molecule (check_stability, utils/evaluation/analyze.py:264-297) -----------
+    def check_stability(self, bd, pos, atomic_numbers, hs=False):
+        """-> (molecule_stable [B] bool, stable_atoms [B] int32, nr_bonds [N] int32), all on the device."""
+        from . import chem_tables as ct
+        dev = pos.device
+        elem = ct.element_index(atomic_numbers).to(torch.int32).to(dev).contiguous()
+        thr = ct.thresholds().to(dev).contiguous()
+        allowed = torch.tensor(ct.ALLOWED_BONDS, dtype=torch.int32, device=dev)
+        nr = torch.empty(bd.n_atoms, dtype=torch.int32, device=dev)
+        st_atoms = torch.empty(bd.n_mols, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.smb_check_stability(C.byref(bd.c), pos.data_ptr(), elem.data_ptr(), thr.data_ptr(), allowed.data_ptr(),
+                                                len(ct.ELEMENTS), int(bool(hs)), nr.data_ptr(), st_atoms.data_ptr(), stream), 'smb_check_stability')
+        sizes = (bd.mol_ptr[1:] - bd.mol_ptr[:-1]).to(torch.int32)
+        return st_atoms == sizes, st_atoms, nr
+
     def decrement_t(self, t_i32):
         stream = torch.cuda.current_stream(t_i32.device).cuda_stream
         _lib.check(self.lib.smb_decrement_t(t_i32.data_ptr(), t_i32.numel(), stream), 'smb_decrement_t')

@@ -111,3 +111,22 @@ def test_final_distributions_indistinguishable(cuda_lib):
               % (precision, p_dist, p_rocs, p_type, p_null))
         assert p_null < 1e-6
         assert p_dist > 0.01 and p_rocs > 0.01 and p_type > 0.01
+
+
+def test_stability_kernel_matches_reference(cuda_lib):
+    from test_gpu_parity import build_model, batch_of
+    from shapemol_b200.engine import BatchDesc
+    from shapemol_b200 import chem_tables as ct
+    cases = torch.load(os.path.join(ROOT, 'tests', 'golden', 'stability.pt'))
+    fx = load_golden('forward_k8_eval.pt')
+    eng = build_model(fx, 'bf16x3', training=False)._engine()
+    for hs in (False, True):
+        cs = [c for c in cases if c['hs'] == hs]
+        sizes = [int(c['pos'].shape[0]) for c in cs]
+        bd = BatchDesc(batch_of(sizes), len(sizes))
+        pos = torch.cat([c['pos'] for c in cs]).cuda()
+        z = torch.cat([c['z'] for c in cs]).cuda()
+        mol_stable, st_atoms, nr = eng.check_stability(bd, pos, z, hs=hs)
+        assert torch.equal(nr.cpu().long(), torch.cat([c['nr_bonds'] for c in cs]))
+        assert st_atoms.cpu().tolist() == [c['nr_stable'] for c in cs]
+        assert mol_stable.cpu().tolist() == [c['stable'] for c in cs]

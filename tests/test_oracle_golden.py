@@ -101,3 +101,16 @@ def test_shape_tanimoto_oracle_matches_reference():
     for c in cases:
         assert abs(float(orc.get_rocs(c['a'], c['b'])) - float(c['rocs'])) < 1e-12
     assert abs(float(orc.get_rocs(cases[-1]['a'], cases[-1]['b'])) - 1.0) < 1e-12      # identical centre sets
+
+
+def test_stability_oracle_and_tables_match_reference():
+    """tests/golden/stability.pt: outputs of the unmodified check_stability (utils/evaluation/analyze.py:264-297)."""
+    from shapemol_b200 import chem_tables as ct
+    cases = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'stability.pt'))
+    thr, allowed = ct.thresholds(), torch.tensor(ct.ALLOWED_BONDS, dtype=torch.int32)
+    assert thr.shape == (3, 10, 10) and bool((thr == thr.transpose(1, 2)).all())
+    for c in cases:
+        stable, nr_stable, n, nr = orc.check_stability(c['pos'], ct.element_index(c['z']), thr, allowed, hs=c['hs'])
+        assert (stable, nr_stable, n) == (c['stable'], c['nr_stable'], c['pos'].shape[0]) and torch.equal(nr, c['nr_bonds'])
+    with pytest.raises(KeyError):
+        ct.element_index(torch.tensor([6, 5]))      # boron is not in the reference's tables
