@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 # Linear(308->128) + Linear(128->128) + <q,k>
 F_REF_EDGE_K = 2 * (308 * 128 + 128 * 128) + 2 * 128
 F_MIN_EDGE_K = 2 * (20 * 128 + 128 * 128) + 2 * 128       # with the first Linear factored to node level
-KERNELS_PER_STEP = 5 + 8 * 9 + 1 + 1 + 1                   # prep, embed, knn, tile list, gate | 8 x (3 node, 4 edge, bn, apply) | head | posterior | t--
+KERNELS_PER_STEP = 4 + 8 * 9 + 1 + 1 + 1                   # prep, embed, knn, gate | 8 x (3 node, 4 edge, bn, apply) | head | posterior | t--
+#                                                            (the tile list is built once: steps after the first reuse it)
 
 
 def ref_like_config(k=32):
