@@ -537,7 +537,6 @@ int launch_role(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
 
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* grid_out, cudaStream_t st) {
   if (a.n_mols <= 0) { if (grid_out) *grid_out = 0; return 0; }
-  if (edge_tc5_supported(d, role, a)) return launch_edge_tc5(role, a, grid_out, st);
   const bool x3 = d.precision == SMB_PREC_BF16X3;
   switch (role) {
     case ROLE_GATE: return x3 ? launch_role<ROLE_GATE, true>(a, grid_out, st) : launch_role<ROLE_GATE, false>(a, grid_out, st);

@@ -1,5 +1,5 @@
 // Warp-specialised tcgen05 / TMEM pipeline for the fused edge kernels (plain-bf16 contraction mode,
-// molecules of <= 32 atoms: the MOSES workload).  Same math as smb_edge_attn.cu / smb_edge_tc5.cu
+// molecules of <= 32 atoms: the MOSES workload).  Same math as smb_edge_attn.cu
 // (BaseX2HAttLayer / BaseH2XAttLayer, models/uni_transformer.py:48-162); this file changes the
 // SCHEDULE: one persistent CTA per SM, a static list of 128-row tiles, and five roles that hand tiles
 // to each other through mbarriers so that global-load latency, the two MMAs and the SIMT epilogues of
@@ -874,7 +874,7 @@ int debug_ws_trace(long long* host_out) {
 }
 
 bool edge_ws_supported(const smb_model_dims& d, int n_max) {
-  static const bool off = getenv("SMB_EDGE_TC5") != nullptr || getenv("SMB_EDGE_LEGACY") != nullptr;   // debugging aids
+  static const bool off = getenv("SMB_EDGE_LEGACY") != nullptr;   // debugging aid: mma.sync kernels in bf16 mode
   return !off && d.precision == SMB_PREC_BF16 && d.hidden == H && n_max >= 1 && n_max <= G && d.k >= 1;
 }
 

@@ -133,10 +133,6 @@ struct EdgeArgs {
 };
 // bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
-// tcgen05 / TMEM implementation (smb_edge_tc5.cu): plain-bf16 mode, molecules of <= 32 atoms
-bool edge_tc5_supported(const smb_model_dims& d, int role, const EdgeArgs& a);
-int launch_edge_tc5(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
-
 // warp-specialised tcgen05 pipeline (smb_edge_ws.cu): plain-bf16 mode, molecules of <= 32 atoms, all three roles together
 bool edge_ws_supported(const smb_model_dims& d, int n_max);
 int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st);

@@ -19,7 +19,7 @@ def errs(a, b):
 
 
 def main():
-    tag = 'legacy' if os.environ.get('SMB_EDGE_LEGACY') else 'tc5' if os.environ.get('SMB_EDGE_TC5') else 'ws'
+    tag = 'legacy' if os.environ.get('SMB_EDGE_LEGACY') else 'ws'
     if os.environ.get('SMB_NODE_LEGACY'):
         tag += '_nl'
     for name in ('k32_train', 'k32_eval', 'k8_train', 'k8_eval', 'tiny_train'):
@@ -51,7 +51,7 @@ def main():
     print(tag, 'ragged 1..27: finite', all(bool(torch.isfinite(x).all()) for x in out.values()), 'ms/forward %.2f' % ((time.time() - t0) / 3 * 1e3))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     torch.save({k: x.cpu() for k, x in out.items()}, os.path.join(ROOT, 'gpurun_out', 'ragged_%s.pt' % tag))
-    for other in ('legacy', 'tc5', 'ws', 'ws_nl'):
+    for other in ('legacy', 'ws', 'ws_nl'):
         f = os.path.join(ROOT, 'gpurun_out', 'ragged_%s.pt' % other)
         if other != tag and os.path.exists(f):
             ref = torch.load(f)
