@@ -91,7 +91,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   pa.inv_bb = fptr(blob, L.inv_bb); pa.inv_w2 = fptr(blob, L.inv_w2); pa.inv_b2 = fptr(blob, L.inv_b2);
   pa.tau = tau; pa.inv = inv;
   float* vn_shape = wptr<float>(ws_base, W.vn_shape);
-  pa.n_layers = d.layers; pa.vn_shape = vn_shape; pa.do_shape = io.reuse_static ? 0 : 1;
+  pa.n_layers = d.layers; pa.vn_shape = H == 128 ? vn_shape : nullptr; pa.do_shape = io.reuse_static ? 0 : 1;
   for (int l = 0; l < d.layers; ++l) { pa.vn_w[l][0] = fptr(blob, L.layer[l].vn_feat); pa.vn_w[l][1] = fptr(blob, L.layer[l].vn_dir); }
   SMB_LAUNCH(launch_prep(pa, st));
 
@@ -102,6 +102,8 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
 
   SMB_TIMED(SMB_PROF_KNN, launch_knn(x, b.mol_ptr, B, d.k, nbr, deg, st));
   if (io.nbr) SMB_CUDA_OK(cudaMemcpyAsync(io.nbr, nbr, (size_t)N * (d.k + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+
+  if (H != 128) return forward_generic(d, blob, L, W, ws_base, b, io, st);   // generic-shape fp32 path
 
   // warp-specialised tcgen05 pipeline for the three attention roles (plain-bf16 mode, <= 32 atoms per molecule)
   const bool ws = edge_ws_supported(d, n_max);
@@ -253,6 +255,7 @@ int smb_type_head(const smb_model_dims* dims, const void* packed_weights_dev, co
   rc = smb::check_batch(batch);
   if (rc) return rc;
   const smb::ModelLayout L = smb::build_layout(*dims);
+  if (dims->hidden != 128) return smb::type_head_generic(*dims, packed_weights_dev, L, batch->n_atoms, h, logits, (cudaStream_t)stream);
   smb::NodeArgs n;
   memset(&n, 0, sizeof(n));
   n.n_atoms = batch->n_atoms; n.atom_mol = batch->atom_mol;

@@ -19,7 +19,8 @@ void set_error(const char* what, cudaError_t e) {
 void set_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 
 int check_dims(const smb_model_dims& d) {
-  if (d.hidden != 128) { set_error_msg("hidden_dim must be 128 (256 is not built yet)"); return SMB_E_UNSUPPORTED; }
+  // hidden 128: tuned tensor-core kernels; any other width (e.g. 256): generic fp32 path (smb_generic.cu)
+  if (d.hidden < 32 || d.hidden > 512 || d.hidden % 32 != 0) { set_error_msg("hidden_dim must be a multiple of 32 in 32..512"); return SMB_E_UNSUPPORTED; }
   if (d.heads != kHeads) { set_error_msg("n_heads must be 16"); return SMB_E_UNSUPPORTED; }
   if (d.layers < 1 || d.layers > kMaxLayers) { set_error_msg("num_layers out of range"); return SMB_E_UNSUPPORTED; }
   if (d.k < 1 || d.k > SMB_MAX_K) { set_error_msg("knn out of range (1..63)"); return SMB_E_TOOBIG; }
@@ -110,6 +111,8 @@ ModelLayout build_layout(const smb_model_dims& d) {
     y.vn_feat = c.take(kHeads * kVnStride * 4);
     y.vn_dir = c.take(kHeads * kVnStride * 4);
   }
+  L.raw = c.off;
+  if (d.hidden != 128) c.take(raw_weights_bytes(d));
   L.total = c.off;
   return L;
 }
@@ -141,6 +144,12 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.bn_part = c.take((size_t)w.bn_part_rows * 32 * 4);
   w.bn_param = c.take(32 * 4);
   w.vn_shape = c.take((size_t)d.layers * b * 96 * 4);
+  if (d.hidden != 128) {
+    const size_t m = n * KS;
+    w.g_hid = c.take(m * H * 4); w.g_out = c.take(m * H * 4); w.g_alpha = c.take(m * kHeads * 4);
+    w.g_rbf = c.take(m * kRbf * 4); w.g_rel = c.take(m * 3 * 4); w.g_idx = c.take(3 * m * 4);
+    w.g_node = c.take(n * H * 4); w.g_bn = c.take(n * 32 * 4);
+  }
   w.tiles = c.take(16 + (size_t)w.max_tiles * 16);
   w.total = c.off;
   return w;
@@ -240,6 +249,11 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
     put(blob, L.inv_w1, get(p + "0.weight"), kShape * kShape); put(blob, L.inv_b1, get(p + "0.bias"), kShape);
     put(blob, L.inv_g, get(p + "1.weight"), kShape); put(blob, L.inv_bb, get(p + "1.bias"), kShape);
     put(blob, L.inv_w2, get(p + "3.weight"), kShape * kShape); put(blob, L.inv_b2, get(p + "3.bias"), kShape);
+  }
+  if (H != 128) {   // generic-shape path: the kernels read the parameters as they are
+    const size_t nn = names.size();
+    for (size_t i = 0; i < nn; ++i) memcpy(blob + L.raw + raw_weight_offset(d, names[i]), hp[i], param_numel(d, names[i]) * 4);
+    return 0;
   }
   // LayerNorm folding (warp-specialised edge pipeline).  For an edge MLP with first Linear W1 / b1 and LayerNorm
   // (gamma, beta):  LN(v)_c = gamma_c (v_c - mean) rstd + beta_c.  Exact algebra:

@@ -139,6 +139,11 @@ int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* 
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 int debug_ws_trace(long long* host_out);   // [8 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
 
+// generic-shape fp32 path (smb_generic.cu): hidden_dim != 128
+int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout& L, const Workspace& W, void* ws_base, const smb_batch& b,
+                    const smb_forward_io& io, cudaStream_t st);
+int type_head_generic(const smb_model_dims& d, const void* blob, const ModelLayout& L, int N, const float* h, float* logits, cudaStream_t st);
+
 int launch_prep(const PrepArgs& a, cudaStream_t st);
 int launch_knn(const float* x, const int* mol_ptr, int n_mols, int k, int* nbr, int* deg, cudaStream_t st);
 int launch_embed(const EmbedArgs& a, cudaStream_t st);

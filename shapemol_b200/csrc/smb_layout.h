@@ -83,12 +83,17 @@ struct ModelLayout {
   EdgeMlpOff gate;      // edge_pred_layer
   NodeMlpOff head;      // v_inference: X=h (K1=H) -> H -> ssp -> classes (padded to 16)
   LayerOff layer[kMaxLayers];
+  size_t raw;           // hidden != 128 only: raw fp32 copy of every parameter (smb_param_name order) for the generic path
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline size_t frag_bytes(const smb_model_dims& d) { return d.precision == SMB_PREC_BF16X3 ? 16 : 8; }
 
 ModelLayout build_layout(const smb_model_dims& d);
+// generic-shape path (smb_generic.cu)
+size_t param_numel(const smb_model_dims& d, const std::string& name);
+size_t raw_weights_bytes(const smb_model_dims& d);
+size_t raw_weight_offset(const smb_model_dims& d, const std::string& name);
 const std::vector<std::string>& param_names(const smb_model_dims& d);
 int check_dims(const smb_model_dims& d);
 
@@ -110,6 +115,12 @@ struct Workspace {
   size_t bn_part;   // [bn_part_rows][32]
   size_t bn_param;  // [32] scale | shift
   size_t vn_shape;  // [L][B][96] shape-embedding part of the VN linear maps
+  // generic-shape path (hidden != 128): dense slot table e = atom * (k+1) + slot, M = N (k+1)
+  size_t g_hid, g_out;     // [M][H]
+  size_t g_alpha;          // [M][heads]
+  size_t g_rbf, g_rel;     // [M][20], [M][3]
+  size_t g_idx;            // int32 [3][M]: destination / source atom, molecule (-1: empty slot)
+  size_t g_node, g_bn;     // [N][H], [N][32]
   size_t tiles;     // [max_tiles] int4 tile descriptors, preceded by the tile count (16 bytes)
   int max_tiles;    // N/4 + B + 8: a tile holds >= 4 destination atoms unless it is the last of its molecule
   int bn_part_rows;

@@ -82,6 +82,31 @@ def test_knn_random_ragged_vs_oracle_bit_exact(cuda_lib):
 
 
 # ---------------------------------------------------------------------------------------------
+def test_forward_hidden256_k48_60_atoms_generic_path(cuda_lib):
+    """BASELINE configs[4] shape (hidden 256, k = 48, molecules of 60 / 52 atoms, train-mode BN): the generic fp32 path
+    (csrc/smb_generic.cu) against the fixture of the unmodified reference."""
+    fx = load_golden('forward_k48_h256_train.pt')
+    m, _ = make_dropin(knn=fx['k'], hidden_dim=256, n_heads=16)
+    missing, unexpected = m.load_state_dict(golden_weights(fx), strict=False)
+    assert not unexpected
+    m = m.cuda().train()
+    out = m(fx['pos'].cuda(), fx['v'].cuda(), batch_of(fx['sizes']), fx['shape'].cuda(), time_step=fx['t'].cuda(), return_all=True)
+    torch.cuda.synchronize()
+    errs = {k: rel_err(out[k], fx[r]) for k, r in (('pred_ligand_pos', 'pred_pos'), ('pred_ligand_h', 'pred_h'), ('pred_ligand_v', 'pred_v'))}
+    print('hidden 256', errs)
+    for k, e in errs.items():
+        assert e < REL_FP32, (k, e)
+    sd = m.state_dict()
+    for l in (0, 7):
+        p = 'refine_net.base_block.%d.h2x_layers.0.shape_linear.batchnorm.bn.' % l
+        assert torch.allclose(sd[p + 'running_mean'].cpu(), fx['bn%d_running_mean' % l], rtol=1e-3, atol=1e-5)
+        assert torch.allclose(sd[p + 'running_var'].cpu(), fx['bn%d_running_var' % l], rtol=5e-3, atol=1e-5)
+    assert out['layer_pred_ligand_v'][0].shape == (sum(fx['sizes']), 15)
+    # two reverse steps through the public API
+    r = m.sample_diffusion(fx['pos'].cuda(), fx['v'].cuda(), batch_of(fx['sizes']), fx['shape'].view(-1, 3).cuda(), num_steps=2, center_pos_mode='none')
+    assert torch.isfinite(r['pos']).all()
+
+
 @pytest.mark.parametrize('name', FWD_H128)
 @pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
 def test_forward_matches_reference_fixture(cuda_lib, name, precision):

@@ -97,9 +97,26 @@ def test_param_enumeration_and_packing_host_side():
     dims2 = _lib.ModelDims(hidden=128, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=_lib.PREC_BF16)
     assert lib.smb_packed_weights_bytes(C.byref(dims2)) < nbytes
     # unsupported configuration -> error code + message, no crash
-    bad = _lib.ModelDims(hidden=64, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=0)
+    bad = _lib.ModelDims(hidden=100, heads=16, layers=8, k=32, classes=15, time_dim=8, timesteps=1000, precision=0)
     assert lib.smb_param_count(C.byref(bad)) == -1
     assert b'hidden' in lib.smb_last_error_string()
+    # hidden != 128 (generic fp32 path): the blob ends with the raw parameters, in enumeration order
+    fx = load_golden('forward_k48_h256_train.pt')
+    d256 = _lib.ModelDims(hidden=256, heads=16, layers=8, k=48, classes=15, time_dim=8, timesteps=1000, precision=_lib.PREC_BF16X3)
+    n2 = lib.smb_param_count(C.byref(d256))
+    names2 = [lib.smb_param_name(C.byref(d256), i).decode() for i in range(n2)]
+    sd2 = synth.synth_state_dict({k: tuple(v) for k, v in fx['shapes'].items()}, 3)
+    host2 = [sd2[k].contiguous() for k in names2]
+    nb2 = lib.smb_packed_weights_bytes(C.byref(d256))
+    blob2 = torch.zeros(nb2, dtype=torch.uint8)
+    assert lib.smb_pack_weights(C.byref(d256), (C.c_void_p * n2)(*[t.data_ptr() for t in host2]), n2, blob2.data_ptr(), nb2) == 0
+    raw_bytes = sum((t.numel() * 4 + 15) // 16 * 16 for t in host2)
+    start = nb2 - (raw_bytes + 255) // 256 * 256          # the region is 256-byte aligned and padded
+    tail = blob2[start:start + raw_bytes].view(torch.float32)
+    off = 0
+    for t in host2:
+        assert torch.equal(tail[off:off + t.numel()], t.flatten()), 'raw parameter copy'
+        off += (t.numel() * 4 + 15) // 16 * 16 // 4
 
 
 def test_product_path_has_no_cpu_fallback():
