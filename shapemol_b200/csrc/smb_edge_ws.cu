@@ -46,8 +46,9 @@ constexpr int LS = 17;                 // padded row stride of per-row head scra
 constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
 // 28 warps = 7 warpgroups, launched at 72 registers per thread and re-balanced per role with setmaxnreg (Regs<ROLE>):
 //   WG0     warps  0-3   P (2 warps, two rows per thread), GEMM1 issuer + loader, GEMM2 issuer     72 (unchanged)
-//   WG1-2   warps  4-11  LN                                                                           88 / 96
-//   WG3-6   warps 12-27  E2: ROLE_XV four groups at 64; ROLE_K / ROLE_V two groups at 96, the rest idle at 24
+//   WG1-2   warps  4-11  LN                                                                           96
+//   WG3-6   warps 12-27  E2: ROLE_XV four groups at 56; ROLE_K / ROLE_V two groups at 96, the rest idle at 24
+// (measured: ROLE_XV 208 us with LN 88 / E2 64, 193 us with 96 / 56; ROLE_K 261 us with LN 88 / E2 104, 242 us with 96 / 96)
 constexpr int P_WARPS = 2, GRP_WARPS = 8, NG_MAX = 4, WARPS = 28, THREADS = WARPS * 32;
 constexpr int MMA_WARP = 2, G2_WARP = 3, LN_WARP0 = 4, E2_WARP0 = LN_WARP0 + GRP_WARPS;
 constexpr int REGS_IDLE = 24;
@@ -70,7 +71,20 @@ template <int ROLE> struct Ring {
   // epilogue groups: ROLE_V's shared memory (z^T operands) has room for two staging areas only
   static constexpr int NG = ROLE == ROLE_GATE ? 0 : ROLE == ROLE_XV ? 4 : 2;
   // register budgets (pool: 7 warpgroups x 72 = 504):  72 + 2 LN + NG E2 + (4 - NG) 24 <= 504
-  static constexpr int REGS_LN = ROLE == ROLE_XV ? 88 : 96, REGS_E2 = ROLE == ROLE_XV ? 64 : 96;
+#ifndef SMB_K_LN
+#define SMB_K_LN 96
+#define SMB_K_E2 96
+#endif
+#ifndef SMB_V_LN
+#define SMB_V_LN 96
+#define SMB_V_E2 96
+#endif
+#ifndef SMB_XV_LN
+#define SMB_XV_LN 96
+#define SMB_XV_E2 56
+#endif
+  static constexpr int REGS_LN = ROLE == ROLE_XV ? SMB_XV_LN : ROLE == ROLE_V ? SMB_V_LN : ROLE == ROLE_K ? SMB_K_LN : 96;
+  static constexpr int REGS_E2 = ROLE == ROLE_XV ? SMB_XV_E2 : ROLE == ROLE_V ? SMB_V_E2 : ROLE == ROLE_K ? SMB_K_E2 : 96;
   static_assert(72 + 2 * REGS_LN + NG * REGS_E2 + (4 - NG) * REGS_IDLE <= 504, "register pool");
   // D2_FULL / E2_DONE mbarriers are indexed by tile % NB2 (the TMEM buffer by tile % ND2).  A parity wait is only
   // unambiguous if the waiter visits every phase of its barrier: an epilogue group sees tiles g, g + NG, ..., so NB2 must
