@@ -291,7 +291,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_v4_ncu_full_summary.txt);
             # only valid for the default workload in bf16 mode
             traffic = 240.0e6 if (args.precision == 'bf16' and args.shapes == 100 and args.per_shape == 50 and args.k == 32 and not args.fixed_atoms) else None
-            roof = {'kernel': 'edge_kernel<ROLE_K> (edge MLP + attention logits + per-destination softmax)',
+            roof = {'kernel': ('edge_ws_kernel<ROLE_K>' if args.precision == 'bf16' else 'edge_kernel<ROLE_K>') + ' (edge MLP + attention logits + per-destination softmax)',
                     'bound': 'tensor', 'achieved': flops / (kms * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
                     'frac': flops / (kms * 1e-3) / 1e12 / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
                     'ms_per_launch': kms, 'launches_per_step': 16, 'share_of_step': 16 * kms / ms,
