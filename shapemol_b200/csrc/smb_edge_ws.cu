@@ -177,7 +177,7 @@ struct Tile {
 };
 
 // timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
-constexpr int TRACE_EVENTS = 13, TRACE_TILES = 128;
+constexpr int TRACE_EVENTS = 15, TRACE_TILES = 128;
 __device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
 #define SMB_TRACE(ev, t, cond) do { if ((a.dbg & 16) && (a.dbg >> 8) == ROLE && blockIdx.x == 0 && (t) < TRACE_TILES && (cond)) g_trace[ev][t] = clock64(); } while (0)
 
@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (t + 1 < nt) fetch_x(Tile(td_a), j_a);
       if (t + 2 < nt) fetch_j(Tile(td_b), j_b);
       if (t + 3 < nt) td_c = __ldg(tiles + t + 3);
+      SMB_TRACE(13, t, tid == 0);
       if (t >= 2) mbar_wait(bar + B_A1_FREE + slot, ((t >> 1) - 1) & 1);
+      SMB_TRACE(14, t, tid == 0);
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = tid + u * (P_WARPS * 32);
