@@ -221,18 +221,30 @@ class ScorePosNet3D(nn.Module):
             point_clouds, _, radius = use_pointcloud_data
             cloud = torch.as_tensor(np.asarray(point_clouds, dtype=np.float64)).to(init_ligand_pos.device).contiguous()
             guidance = dict(cloud=cloud, radius=float(radius), grad_step=int(grad_step), ratio=0.2)
-        if center_pos_mode not in (None, 'none'):
-            raise NotImplementedError("center_pos_mode=%r is not built (shipped configs use 'none')" % (center_pos_mode,))
+        offset = None
+        if center_pos_mode == 'center':
+            # center_pos (reference :52-60, :547): per-molecule mean of the initial positions, added back to the final state
+            # and to pos_traj (:675-684).  Once per sampling run: host-side glue, not part of the step.
+            nb = int(batch_ligand.max().item()) + 1 if batch_ligand.numel() else 0
+            cnt = torch.bincount(batch_ligand, minlength=nb).clamp_min(1).to(init_ligand_pos.dtype)
+            offset = torch.zeros(nb, 3, dtype=init_ligand_pos.dtype, device=init_ligand_pos.device).index_add_(0, batch_ligand, init_ligand_pos)
+            offset = offset / cnt[:, None]
+            init_ligand_pos = init_ligand_pos - offset[batch_ligand]
+        elif center_pos_mode not in (None, 'none'):
+            raise NotImplementedError('center_pos_mode=%r' % (center_pos_mode,))      # as the reference (:58-59)
         eng = self._engine()
         sampler = Sampler(eng, init_ligand_pos, init_ligand_v, batch_ligand, ligand_shape, num_steps=num_steps,
                           noise=self.smb_noise, seed=self.smb_seed, keep_traj=self.smb_keep_traj, use_graph=self.smb_use_graph,
                           guidance=guidance)
         pos, v = sampler.run(progress=lambda it: tqdm(it, desc='sampling', total=num_steps))
+        if offset is not None:
+            pos = pos + offset[batch_ligand]
         out = {'pos': pos, 'v': v.to(torch.long), 'pos_traj': [], 'pos_cond_traj': [], 'pos_uncond_traj': [], 'v_traj': [],
                'v_cond_traj': [], 'v_uncond_traj': [], 'v0_traj': [], 'vt_traj': []}
         if self.smb_keep_traj:
             tr = sampler.traj
-            out['pos_traj'] = list(tr['pos'].cpu().unbind(0))                      # CPU tensors, as the reference (:680)
+            pt = tr['pos'] if offset is None else tr['pos'] + offset[batch_ligand][None]
+            out['pos_traj'] = list(pt.cpu().unbind(0))                             # CPU tensors, as the reference (:680)
             out['v_traj'] = list(tr['v'].cpu().to(torch.long).unbind(0))
             out['v0_traj'] = list(tr['v0'].cpu().unbind(0))
             out['vt_traj'] = list(tr['vt'].cpu().unbind(0))

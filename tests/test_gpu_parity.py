@@ -357,3 +357,28 @@ def test_host_stepper_graph_equals_eager(cuda_lib):
         assert p.shape == (N, 3) and bool(torch.isfinite(p).all())
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert not torch.equal(outs[0][0], fx['pos'])
+
+
+def test_center_pos_mode_center(cuda_lib):
+    """center_pos_mode='center' (reference :52-60,:547,:675-684): sampling in each molecule's centred frame, offsets added back."""
+    fx = load_golden('forward_k32_eval.pt')
+    sizes = fx['sizes']
+    batch = batch_of(sizes)
+    g = torch.Generator().manual_seed(4)
+    pos0 = (fx['pos'] + 5.0 * torch.randn(len(sizes), 3, generator=g)[batch.cpu()]).cuda()     # molecules far from the origin
+    kw = dict(init_ligand_v=fx['v'].cuda(), batch_ligand=batch, ligand_shape=fx['shape'].view(-1, 3).cuda(), num_steps=4)
+    res = {}
+    for mode in ('center', 'none'):
+        m = build_model(fx, training=False)
+        m.smb_noise, m.smb_seed, m.smb_keep_traj = 'philox', 5, True
+        if mode == 'center':
+            res[mode] = m.sample_diffusion(init_ligand_pos=pos0, center_pos_mode='center', **kw)
+        else:
+            off = torch.zeros(len(sizes), 3, device='cuda').index_add_(0, batch, pos0) / torch.tensor(sizes, device='cuda')[:, None]
+            r = m.sample_diffusion(init_ligand_pos=pos0 - off[batch], center_pos_mode='none', **kw)
+            res[mode] = dict(r, pos=r['pos'] + off[batch], pos_traj=[p + off[batch].cpu() for p in r['pos_traj']])
+    assert torch.allclose(res['center']['pos'], res['none']['pos'], atol=1e-5)
+    assert torch.equal(res['center']['v'], res['none']['v'])
+    assert torch.allclose(res['center']['pos_traj'][-1], res['none']['pos_traj'][-1], atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        m.sample_diffusion(init_ligand_pos=pos0, center_pos_mode='bogus', **kw)
