@@ -382,3 +382,28 @@ def test_center_pos_mode_center(cuda_lib):
     assert torch.allclose(res['center']['pos_traj'][-1], res['none']['pos_traj'][-1], atol=1e-5)
     with pytest.raises(NotImplementedError):
         m.sample_diffusion(init_ligand_pos=pos0, center_pos_mode='bogus', **kw)
+
+
+@pytest.mark.parametrize('hidden,k', [(64, 8), (192, 20)])
+def test_generic_path_other_widths_vs_oracle(cuda_lib, hidden, k):
+    """The generic fp32 path (csrc/smb_generic.cu) for widths without a reference fixture, against the pinned oracle."""
+    import synth
+    from oracle import shapemol_oracle as orc
+    m, _ = make_dropin(knn=k, hidden_dim=hidden, n_heads=16)
+    shapes = {n: tuple(v.shape) for n, v in m.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, 11)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(hidden)
+    sizes = [1, 2, 17, 33, 9]
+    N = sum(sizes)
+    pos, v = 2.0 * torch.randn(N, 3, generator=g), torch.randint(0, 15, (N,), generator=g)
+    shape = 0.07 * torch.randn(len(sizes), 32, 3, generator=g)
+    t = torch.randint(0, 1000, (len(sizes),), generator=g)
+    out = m(pos.cuda(), v.cuda(), batch_of(sizes), shape.cuda(), time_step=t.cuda())
+    cfg = dict(orc.DEFAULT_CFG, knn=k, hidden_dim=hidden, n_heads=16)
+    full = dict(m.state_dict())
+    with torch.no_grad():
+        ex, eh, el = orc.forward({n: w.detach().cpu() for n, w in full.items()}, cfg, pos, v, orc.mol_ptr_from_sizes(sizes), shape, t, training=False)
+    for name, a, b in (('pos', out['pred_ligand_pos'], ex), ('h', out['pred_ligand_h'], eh), ('v', out['pred_ligand_v'], el)):
+        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
