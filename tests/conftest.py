@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def pytest_sessionstart(session):
+    """The in-tree library is a build artefact (git-ignored): (re)build it when it is missing or older than its sources
+    (incremental, a no-op otherwise; nvcc cross-compiles sm_100a without a GPU)."""
+    try:
+        from shapemol_b200 import build as _build
+        _build.build()
+    except Exception as e:     # no nvcc: the tests that need the library report it themselves
+        print('shapemol_b200: library build skipped (%s)' % e)
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), map_location='cpu', weights_only=False)
 
