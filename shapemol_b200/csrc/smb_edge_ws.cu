@@ -54,7 +54,7 @@ constexpr int MMA_WARP = 2, G2_WARP = 3, LN_WARP0 = 4, E2_WARP0 = LN_WARP0 + GRP
 constexpr int REGS_IDLE = 24;
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
-constexpr int BAR_LN = 1, BAR_E2 = 2;   // named barriers (0 is __syncthreads); E2 group g uses BAR_E2 + g
+constexpr int BAR_LN = 1, BAR_E2 = 2, BAR_LNQ = 6;   // named barriers (0 is __syncthreads); E2 group g uses BAR_E2 + g, LN quadrant q BAR_LNQ + q
 constexpr int E2_GRP_THREADS = 128;
 constexpr int P_ROWS = TM / (P_WARPS * 32);   // rows of a tile per producer thread
 constexpr int GRP_THREADS = GRP_WARPS * 32;
@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const float sq = ln_sumsq64(v);
       float* st = s_stat + zb * (2 * TM);          // double-buffered: a fast thread may already be one tile ahead
       st[half * TM + r] = sq;
-      named_sync(BAR_LN, GRP_THREADS);
+      // the two column halves of a row live in warps (qd) and (qd + 4): a 64-thread barrier per TMEM lane quadrant
+      named_sync(BAR_LNQ + qd, 64);
       const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
       if (ROLE == ROLE_GATE) {
         // e_w = sigmoid(w2 . relu(LN(.)) + b2)   (uni_transformer.py:475-481): each half-row thread dots its 64 columns
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
         float* sd = reinterpret_cast<float*>(smem + P::o_e2) + zb * (2 * TM);
         sd[half * TM + r] = dot;
-        named_sync(BAR_LN, GRP_THREADS);
+        named_sync(BAR_LNQ + qd, 64);
         if (half == 0) {
           const Tile T(__ldg(tiles + t));
           if (r < T.rows()) {

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
           const float sq = ln_sumsq64(v);
           float* st = s_stat + (it & 1) * (2 * TM);
           st[half * TM + r] = sq;
-          named_sync(BAR_LN, E_THREADS);
+          named_sync(BAR_LN + qd, 64);   // the row's other column half is in the warp of the same TMEM lane quadrant
           const float rstd = rsqrtf((sq + st[(half ^ 1) * TM + r]) * (1.f / H) + 1e-5f);
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
