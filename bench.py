@@ -212,8 +212,6 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
-    clocks.stop_flag = True
-    clocks.join(timeout=3)
     if world > 1:
         tms = torch.tensor([ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -253,6 +251,8 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
+    clocks.stop_flag = True          # sampled through both timed regions (device-resident loop and host-buffer loop)
+    clocks.join(timeout=3)
     if world > 1:
         tms = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
