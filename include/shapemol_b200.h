@@ -13,8 +13,10 @@
  *     library never allocates or frees device memory; scratch space is a caller-provided workspace
  *     sized by smb_workspace_bytes();
  *   - all work is enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*),
- *     no host synchronisation, no global mutable state: safe to capture into a CUDA graph;
- *   - the caller selects the device (cudaSetDevice) before calling;
+ *     no host synchronisation: safe to capture into a CUDA graph.  The only process-wide state is a per-device cache of
+ *     idempotent launch configuration (maximum dynamic shared memory per kernel, SM count) and the per-thread error string;
+ *   - the caller selects the device (cudaSetDevice) before calling: kernels are configured and launched on the CURRENT
+ *     device, which must own every pointer passed in;
  *   - no CPU fallback, no multi-backend dispatch: unsupported configuration => SMB_E_UNSUPPORTED.
  */
 #ifndef SHAPEMOL_B200_H
@@ -187,10 +189,6 @@ SMB_API int smb_posterior_step(const smb_model_dims* dims, const smb_batch* batc
                        void* stream);
 
 /* t[b] -= 1 on the device (keeps the sampling loop free of host syncs / graph-capturable). */
-/* Debug aid (timing experiments, SMB_WS_DBG & 16): clock64 stamps [8 events][128 tiles] of CTA 0 of the last
- * warp-specialised edge kernel.  Not part of the reference-facing surface. */
-SMB_API int smb_debug_ws_trace(int64_t* host_out);
-
 SMB_API int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream);
 
 /* ---- point-cloud shape guidance ----------------------------------------------------

@@ -81,7 +81,6 @@ EXPORTS = {
     'smb_pointcloud_guidance': (C.c_int, [C.POINTER(Batch), C.POINTER(GuidanceIO), _fp]),
     'smb_check_stability': (C.c_int, [C.POINTER(Batch), _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp]),
     'smb_shape_tanimoto': (C.c_int, [C.POINTER(Batch), _fp, _fp, _fp, C.c_int32, C.c_double, C.c_double, C.c_double, _fp, _fp]),
-    'smb_debug_ws_trace': (C.c_int, [_fp]),
     'smb_encoder_workspace_bytes': (C.c_size_t, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32]),
     'smb_vn_dgcnn_encode': (C.c_int, [C.POINTER(EncoderWeights), _fp, C.c_int32, C.c_int32, _fp, _fp, C.c_size_t, _fp]),
 }

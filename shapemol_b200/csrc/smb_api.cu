@@ -327,7 +327,10 @@ int smb_shape_tanimoto(const smb_batch* batch, const float* pos, const double* r
   return rc;
 }
 
-int smb_debug_ws_trace(int64_t* host_out) { return smb::debug_ws_trace(reinterpret_cast<long long*>(host_out)); }
+#ifdef SMB_DEBUG
+// -DSMB_DEBUG builds only (not declared in include/shapemol_b200.h): role trace of the warp-specialised edge pipeline
+__attribute__((visibility("default"))) int smb_debug_ws_trace(int64_t* host_out) { return smb::debug_ws_trace(reinterpret_cast<long long*>(host_out)); }
+#endif
 
 int smb_decrement_t(int32_t* t, int32_t n_mols, void* stream) {
   if (n_mols > 0 && !t) { smb::set_error_msg("smb_decrement_t: null pointer"); return SMB_E_BADARG; }

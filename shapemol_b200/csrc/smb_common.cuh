@@ -12,10 +12,48 @@
     if (_e != cudaSuccess) { smb::set_error(#expr, _e); return (int)_e; }            \
   } while (0)
 
+// Timing-ablation switches (EdgeArgs::dbg / NodeArgs::dbg bit masks, results are wrong when set) and the role trace exist
+// only in -DSMB_DEBUG builds (SMB_NVCC_EXTRA=-DSMB_DEBUG python -m shapemol_b200.build --force); release builds compile
+// them out.
+#ifdef SMB_DEBUG
+#define SMB_DBG(args, bit) (((args).dbg & (bit)) != 0)
+#else
+#define SMB_DBG(args, bit) false
+#endif
+
 namespace smb {
 
 void set_error(const char* what, cudaError_t e);
 void set_error_msg(const char* msg);
+
+// ---- per-device launch configuration ----------------------------------------------------
+// cudaFuncSetAttribute and the SM count belong to the CURRENT device, so both are cached per device ordinal
+// (idempotent values: a racing first use from two host threads is benign).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+template <class Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&cache)[kMaxDevices]) {
+  const int d = current_device_slot();
+  if (cache[d] < bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    cache[d] = bytes;
+  }
+  return 0;
+}
+inline int device_sm_count() {
+  static int cache[kMaxDevices] = {};
+  const int d = current_device_slot();
+  if (cache[d] == 0) {
+    int n = 0;
+    cache[d] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cache[d];
+}
 
 // ---- bf16 split helpers -------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 significant bits ("bf16x3" products

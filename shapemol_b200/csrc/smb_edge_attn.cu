@@ -502,29 +502,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) edge_kernel(EdgeArgs a) {
   }
 }
 
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_num_sms = n;
-    else
-      g_num_sms = 148;
-  }
-  return g_num_sms;
-}
 
 template <int ROLE, bool X3>
 int launch_role(const EdgeArgs& a, int* bn_rows_out, cudaStream_t st) {
   const SmemPlan P = plan_smem(ROLE, X3, a.n_max, a.k);
   if (P.total > 227 * 1024) { set_error_msg("edge kernel: shared memory plan exceeds 227 KB"); return SMB_E_TOOBIG; }
-  static size_t configured = 0;
-  if (configured < P.total) {
-    cudaError_t e = cudaFuncSetAttribute(edge_kernel<ROLE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total);
-    if (e != cudaSuccess) return (int)e;
-    configured = P.total;
-  }
-  int grid = num_sms();
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem(edge_kernel<ROLE, X3>, P.total, configured)) return rc;
+  int grid = device_sm_count();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
   const int n_groups = (a.n_mols + P.mols - 1) / P.mols;
   if (grid > n_groups) grid = n_groups;

@@ -43,7 +43,8 @@ constexpr int A1_SBO = (K1 / 8) * 128; // 1536
 constexpr int A1_BYTES = TM * K1 * 2;  // 24576
 constexpr int AB_BYTES = 2 * G * H * 2;  // 16384: A-tile | B-tile, each [32 k][128 n] MN-major
 constexpr int LS = 17;                 // padded row stride of per-row head scratch
-constexpr int NDMAX = 16;              // destinations per tile (deg >= 8 -> 16; deg < 8 -> n <= 8)
+constexpr int NDMAX = 8;               // destinations per tile: min(128 / deg, NDMAX) (the epilogues' staging areas and the
+                                       // per-tile query operand of ROLE_K are sized for it; small-k graphs get 8 x deg-row tiles)
 // 28 warps = 7 warpgroups, launched at 72 registers per thread and re-balanced per role with setmaxnreg (Regs<ROLE>):
 //   WG0     warps  0-3   P (2 warps, two rows per thread), GEMM1 issuer + loader, GEMM2 issuer     72 (unchanged)
 //   WG1-2   warps  4-11  LN                                                                           96
@@ -179,7 +180,7 @@ struct Tile {
 // timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
 constexpr int TRACE_EVENTS = 15, TRACE_TILES = 128;
 __device__ long long g_trace[TRACE_EVENTS][TRACE_TILES];
-#define SMB_TRACE(ev, t, cond) do { if ((a.dbg & 16) && (a.dbg >> 8) == ROLE && blockIdx.x == 0 && (t) < TRACE_TILES && (cond)) g_trace[ev][t] = clock64(); } while (0)
+#define SMB_TRACE(ev, t, cond) do { if (SMB_DBG(a, 16) && (a.dbg >> 8) == ROLE && blockIdx.x == 0 && (t) < TRACE_TILES && (cond)) g_trace[ev][t] = clock64(); } while (0)
 
 template <int ROLE>
 __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = tid + u * (P_WARPS * 32);
-        if (r < T.rows() && !((a.dbg & 4) && t >= 2)) {
+        if (r < T.rows() && !(SMB_DBG(a, 4) && t >= 2)) {
           unsigned char* arow = s_a1 + slot * A1_BYTES + (r >> 3) * A1_SBO + (r & 7) * 16;
           float e[20];
           rbf20(dist[u], e);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       // z[zb] (TMEM columns / smem operand) was last read by GEMM2(t - 2)
       if (t >= 2) mbar_wait(bar + B_D2_FULL + (t - 2) % NB2, ((t - 2) / NB2) & 1);
       // two passes of 32 columns keep the packed output at 16 registers
-      if (!(a.dbg & 2))
+      if (!SMB_DBG(a, 2))
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
         uint32_t zp[16];
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
       named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
-      if (a.dbg & 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); named_sync(bar_id, E2_GRP_THREADS); continue; }
+      if (SMB_DBG(a, 1)) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); named_sync(bar_id, E2_GRP_THREADS); continue; }
 
       if (ROLE == ROLE_K) {
         float l[16];
@@ -809,7 +810,7 @@ __device__ __forceinline__ int tiles_of(int n, int k) {
   if (n <= 0) return 0;
   const int deg = min(k, n - 1);
   if (deg == 0) return 1;
-  const int per = TM / deg;
+  const int per = min(TM / deg, NDMAX);
   return (n + per - 1) / per;
 }
 
@@ -845,7 +846,7 @@ __global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict
     const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
     if (n <= 0) continue;
     const int deg = min(k, n - 1);
-    const int per = deg > 0 ? TM / deg : 1;
+    const int per = deg > 0 ? min(TM / deg, NDMAX) : 1;
     const int recip = deg > 0 ? 65536 / deg + 1 : 0;
     for (int d0 = 0; d0 < n; d0 += per) {
       const int nd = min(per, n - d0);
@@ -854,30 +855,18 @@ __global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict
   }
 }
 
-int g_sms = 0;
-int sms() {
-  if (g_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sms = n;
-    else
-      g_sms = 148;
-  }
-  return g_sms;
-}
-
 template <int ROLE>
 int launch_ws(const EdgeArgs& a_in, int* bn_rows_out, cudaStream_t st) {
-  static const int dbg = getenv("SMB_WS_DBG") ? atoi(getenv("SMB_WS_DBG")) : 0;
   EdgeArgs a = a_in;
+#ifdef SMB_DEBUG
+  static const int dbg = getenv("SMB_WS_DBG") ? atoi(getenv("SMB_WS_DBG")) : 0;
   a.dbg = dbg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(edge_ws_kernel<ROLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<ROLE>::total);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  int grid = sms();
+#else
+  a.dbg = 0;
+#endif
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem(edge_ws_kernel<ROLE>, Plan<ROLE>::total, configured)) return rc;
+  int grid = device_sm_count();
   if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
   if (bn_rows_out) *bn_rows_out = grid;
   edge_ws_kernel<ROLE><<<grid, THREADS, Plan<ROLE>::total, st>>>(a);
@@ -886,13 +875,18 @@ int launch_ws(const EdgeArgs& a_in, int* bn_rows_out, cudaStream_t st) {
 
 }  // namespace
 
+#ifdef SMB_DEBUG
 int debug_ws_trace(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * TRACE_EVENTS * TRACE_TILES);
 }
+#endif
 
 bool edge_ws_supported(const smb_model_dims& d, int n_max) {
+#ifdef SMB_DEBUG
   static const bool off = getenv("SMB_EDGE_LEGACY") != nullptr;   // debugging aid: mma.sync kernels in bf16 mode
-  return !off && d.precision == SMB_PREC_BF16 && d.hidden == H && n_max >= 1 && n_max <= G && d.k >= 1;
+  if (off) return false;
+#endif
+  return d.precision == SMB_PREC_BF16 && d.hidden == H && n_max >= 1 && n_max <= G && d.k >= 1;
 }
 
 int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st) {

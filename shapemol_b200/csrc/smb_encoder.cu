@@ -419,12 +419,8 @@ static int launch_knn_t(const float* feat, size_t row_stride, int segs, int seg_
   constexpr int R = 8 * RM;
   const int Ppad = (P + 127) / 128 * 128;
   const size_t smem = ((size_t)R * Ppad + 32 * (R + 1) + 32 * 132) * 4;
-  static size_t configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(enc_knn_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem(enc_knn_kernel<RM>, smem, configured)) return rc;
   const int grid = B * ((P + R - 1) / R);
   enc_knn_kernel<RM><<<grid, 256, smem, st>>>(feat, row_stride, segs, seg_len, seg_stride, xx, P, k, idx);
   return (int)cudaGetLastError();

@@ -137,7 +137,7 @@ int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_ro
 bool edge_ws_supported(const smb_model_dims& d, int n_max);
 int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st);
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
-int debug_ws_trace(long long* host_out);   // [8 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
+int debug_ws_trace(long long* host_out);   // -DSMB_DEBUG builds: [15 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
 
 // generic-shape fp32 path (smb_generic.cu): hidden_dim != 128
 int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout& L, const Workspace& W, void* ws_base, const smb_batch& b,

@@ -294,12 +294,8 @@ int launch_mode(const NodeArgs& a, cudaStream_t st) {
   constexpr int KSB = (MODE == 0 ? 160 : 128) / 16;
   constexpr int FB = X3 ? 16 : 8;
   const size_t smem = (size_t)2 * NT_CHUNK * (KSB > KS2 ? KSB : KS2) * 32 * FB + 2 * H * 4;
-  static bool configured = false;   // benign race: attribute set is idempotent
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(node_mlp_kernel<MODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem(node_mlp_kernel<MODE, X3>, smem, configured)) return rc;
   const int grid = (a.n_atoms + 127) / 128;
   node_mlp_kernel<MODE, X3><<<grid, 256, smem, st>>>(a);
   return (int)cudaGetLastError();

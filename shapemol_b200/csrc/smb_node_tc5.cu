@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
       for (int j = 0; j < jobs; ++j) {
         const int slot = j % NWS;
         if (j >= NWS) mbar_wait(bar + B_W_FREE + slot, ((j / NWS) - 1) & 1);
-        if ((a.dbg & 1) && j >= NWS) { mbar_arrive(bar + B_W_FULL + slot); c = c + 1 == N_CH ? 0 : c + 1; continue; }   // timing: no weight streaming
+        if (SMB_DBG(a, 1) && j >= NWS) { mbar_arrive(bar + B_W_FULL + slot); c = c + 1 == N_CH ? 0 : c + 1; continue; }   // timing: no weight streaming
         mbar_arrive_expect_tx(bar + B_W_FULL + slot, WCH_BYTES);
         bulk_g2s(s_w + slot * WCH_BYTES, src + (size_t)c * WCH_BYTES, WCH_BYTES, bar + B_W_FULL + slot);
         c = c + 1 == N_CH ? 0 : c + 1;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
         for (int q = 0; q < RPB; ++q) {
           const int rb = rp * RPB + q;
           const int grow = tile * TM + xw * 32 + rb * 8 + rr;
-          if (mol[rb] >= 0 && !(a.dbg & 4)) {
+          if (mol[rb] >= 0 && !SMB_DBG(a, 4)) {
             // row-major [N][128] or tile image [block][32 column groups][128 rows][4] (NodeArgs::xa_image): eight consecutive
             // columns are two float4 pieces `pst` apart; the next 32 columns are 8 pieces further
             const int rt = grow - tile * TM;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
           fence_before_sync();
           mbar_arrive(bar + B_Z_FULL);
         } else if (s == G2_STEP) {
-          if (valid && !(a.dbg & 2)) {
+          if (valid && !SMB_DBG(a, 2)) {
             // MODE 0: q goes out in the tile image [128-row block][32 column groups][128 rows][4 floats] (kQImage in smb_layout.h): a
             // warp's 32 rows store 512 contiguous bytes per column group instead of 32 scattered 16-byte pieces; the K edge role
             // gathers its destinations' rows from it with 16-byte cp.async pieces.  MODE 1: h' stays row-major [N][128].
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
                                        __uint_as_float(v[e + 3]) + bb.w);
             }
           }
-        } else if (MODE == 0 && valid && !(a.dbg & 2)) {
+        } else if (MODE == 0 && valid && !SMB_DBG(a, 2)) {
           const int part = s - 1;
           unsigned char* dst = img_row + (size_t)part * mn * 256 + (size_t)(half * 8) * mn * 16;
 #pragma unroll
@@ -321,27 +321,28 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
 }  // namespace
 
 bool node_tc5_supported(const smb_model_dims& d, int n_max) {
-  static const bool off = getenv("SMB_NODE_LEGACY") != nullptr;   // debugging aid
-  return !off && edge_ws_supported(d, n_max);
+#ifdef SMB_DEBUG
+  static const bool off = getenv("SMB_NODE_LEGACY") != nullptr;   // debugging aid: mma.sync node kernels in bf16 mode
+  if (off) return false;
+#endif
+  return edge_ws_supported(d, n_max);
 }
 
 template <int MODE>
 static int launch_tc5(const NodeArgs& a, cudaStream_t st) {
   if (a.n_atoms <= 0) return 0;
-  static bool configured = false;
-  static int n_sm = 148;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(node_tc5_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::SMEM_TOTAL);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) n_sm = n;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem(node_tc5_kernel<MODE>, Cfg<MODE>::SMEM_TOTAL, configured)) return rc;
+  const int n_sm = device_sm_count();
   const int n_tiles = (a.n_atoms + TM - 1) / TM;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  static const int dbg = getenv("SMB_NODE_DBG") ? atoi(getenv("SMB_NODE_DBG")) : 0;
   NodeArgs b = a;
+#ifdef SMB_DEBUG
+  static const int dbg = getenv("SMB_NODE_DBG") ? atoi(getenv("SMB_NODE_DBG")) : 0;   // timing ablations (results are wrong when set)
   b.dbg = dbg;
+#else
+  b.dbg = 0;
+#endif
   node_tc5_kernel<MODE><<<grid, THREADS, Cfg<MODE>::SMEM_TOTAL, st>>>(b);
   return (int)cudaGetLastError();
 }

@@ -149,8 +149,9 @@ class ScorePosNet3D(nn.Module):
         from shapemol_b200.engine import BatchDesc
         key = (batch_ligand.data_ptr(), batch_ligand._version, batch_ligand.numel(), str(batch_ligand.device))
         c = self._smb_batch_cache
-        if c is None or c[0] != key:
-            c = (key, BatchDesc(batch_ligand))
+        # the cache holds the keyed tensor itself: while it is alive the allocator cannot hand its address to another batch
+        if c is None or c[0] != key or c[2] is not batch_ligand:
+            c = (key, BatchDesc(batch_ligand), batch_ligand)
             object.__setattr__(self, '_smb_batch_cache', c)
         return c[1]
 
@@ -243,11 +244,12 @@ class ScorePosNet3D(nn.Module):
                'v_cond_traj': [], 'v_uncond_traj': [], 'v0_traj': [], 'vt_traj': []}
         if self.smb_keep_traj:
             tr = sampler.traj
-            pt = tr['pos'] if offset is None else tr['pos'] + offset[batch_ligand][None]
-            out['pos_traj'] = list(pt.cpu().unbind(0))                             # CPU tensors, as the reference (:680)
-            out['v_traj'] = list(tr['v'].cpu().to(torch.long).unbind(0))
-            out['v0_traj'] = list(tr['v0'].cpu().unbind(0))
-            out['vt_traj'] = list(tr['vt'].cpu().unbind(0))
+            # host tensors [S,N,.] filled chunk by chunk while the loop ran (engine.Sampler._drain)
+            pt = tr['pos'] if offset is None else tr['pos'] + offset[batch_ligand].cpu()[None]
+            out['pos_traj'] = list(pt.unbind(0))                                   # CPU tensors, as the reference (:680)
+            out['v_traj'] = list(tr['v'].to(torch.long).unbind(0))
+            out['v0_traj'] = list(tr['v0'].unbind(0))
+            out['vt_traj'] = list(tr['vt'].unbind(0))
             out['pos_cond_traj'] = list(tr['pos_cond'].unbind(0))                  # device tensors (:645-646)
             out['v_cond_traj'] = list(tr['v_cond'].unbind(0))
         return out

@@ -89,8 +89,18 @@ class DenoiseEngine:
             self._packed_key = key
         return self._packed
 
-    def workspace(self, dims, n_atoms, n_mols, device):
+    def workspace(self, dims, n_atoms, n_mols, device, owner=None):
+        """Per-step scratch.  `owner` (a Sampler / HostStepper) gets a workspace of its own: a captured CUDA graph bakes the
+        workspace pointer in, so a later, larger batch evaluated through the same engine must not reallocate it."""
         need = self.lib.smb_workspace_bytes(C.byref(dims), n_atoms, n_mols)
+        if owner is not None:
+            ws = getattr(owner, '_ws', None)
+            if ws is None or ws.numel() < need or ws.device != device:
+                if getattr(owner, 'graph', None) is not None or getattr(owner, '_graph', None) is not None:
+                    raise _lib.SmbError('workspace of a captured step graph cannot grow; build a new Sampler / HostStepper')
+                ws = torch.empty(need, dtype=torch.uint8, device=device)
+                owner._ws = ws
+            return ws
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
@@ -100,11 +110,13 @@ class DenoiseEngine:
 
     # ---- one network evaluation --------------------------------------------------------------
     def forward(self, pos, v_i32, bd, shape, t_i32, pred_pos, pred_h, pred_v, h0=None, nbr=None, training=None, prof=None,
-                reuse_static=False):
+                reuse_static=False, owner=None):
+        if bd.n_atoms == 0:
+            return                      # empty batch (e.g. a rank whose shard holds no molecule): nothing to enqueue
         dims = self.dims()
         dev = pos.device
         blob = self.packed_weights(dev)
-        ws = self.workspace(dims, bd.n_atoms, bd.n_mols, dev)
+        ws = self.workspace(dims, bd.n_atoms, bd.n_mols, dev, owner)
         io = _lib.ForwardIO()
         io.pos, io.v, io.shape, io.t = pos.data_ptr(), v_i32.data_ptr(), shape.data_ptr(), t_i32.data_ptr()
         io.pred_pos, io.pred_h, io.pred_v = pred_pos.data_ptr(), pred_h.data_ptr(), pred_v.data_ptr()
@@ -119,7 +131,8 @@ class DenoiseEngine:
         io.training = int(self.module.training if training is None else training)
         # step-independent workspace contents (invariant shape embedding, VN shape maps, tile list) are kept only if the
         # previous full evaluation used the same batch descriptor, shape tensor, workspace and packed weights
-        key = (id(bd), shape.data_ptr(), ws.data_ptr(), blob.data_ptr())
+        # (the shape tensor's version counter catches in-place updates of the condition latents)
+        key = (id(bd), shape.data_ptr(), shape._version, ws.data_ptr(), blob.data_ptr())
         reuse = bool(reuse_static) and key == self._static_key
         self._static_key = key
         io.reuse_static = int(reuse)
@@ -127,9 +140,10 @@ class DenoiseEngine:
             cls, events = prof
             handles = (C.c_void_p * len(events))(*[ev.cuda_event for ev in events])
             io.prof_kernel, io.prof_capacity, io.prof_events = _lib.PROF[cls], len(events) // 2, handles
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.lib.smb_forward(C.byref(dims), blob.data_ptr(), C.byref(bd.c), C.byref(io), ws.data_ptr(), ws.numel(), stream),
-                   'smb_forward')
+        with torch.cuda.device(dev):     # the launchers configure / launch on the CURRENT device
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.lib.smb_forward(C.byref(dims), blob.data_ptr(), C.byref(bd.c), C.byref(io), ws.data_ptr(), ws.numel(), stream),
+                       'smb_forward')
 
     def type_head(self, h, bd, logits):
         dims = self.dims()
@@ -217,17 +231,24 @@ class Sampler:
     """Reverse-diffusion loop (ScorePosNet3D.sample_diffusion default branch) with persistent device
     state, no host synchronisation inside the loop and the step captured in a CUDA graph.
 
-    While a Sampler is running (and in particular while its captured graph is replayed) no other batch may be evaluated
-    through the same engine: from the second step on the step-independent workspace contents are reused.
+    A Sampler owns its workspace (the captured graph bakes its address in), so other batches may be evaluated through the
+    same engine while it exists.
 
     noise = 'torch'  : per step torch.randn_like(pos) then torch.rand(N, C) from the device's default
                        generator -- the reference's draw order, so torch.manual_seed(s) reproduces it;
             'philox' : in-kernel Philox4x32 keyed by (seed, global atom index, t)   (throughput mode);
             callable : noise(step) -> (randn [N,3], rand [N,C])                    (parity tests).
+
+    Trajectories (keep_traj=True; reference :671-681): the four lists the reference moves to the CPU every step (pos, v,
+    v0, vt) are recorded into a double-buffered device ring of `traj_chunk` steps and drained to host tensors [S,N,.] on a
+    side stream, one D2H per list per chunk, while the next chunk's steps run; the two lists the reference keeps on the
+    device (pos_cond, v_cond) are device tensors [S,N,.].
     """
 
+    HOST_KEYS = ('pos', 'v', 'v0', 'vt')
+
     def __init__(self, engine, init_pos, init_v, batch_ligand, shape, num_steps=None, noise='torch', seed=0, atom_offset=0,
-                 keep_traj=True, use_graph=True, n_mols=None, guidance=None):
+                 keep_traj=True, use_graph=True, n_mols=None, guidance=None, traj_chunk=None):
         m = engine.module
         self.e = engine
         dev = init_pos.device
@@ -237,7 +258,7 @@ class Sampler:
         self.num_steps = T if num_steps is None else int(num_steps)
         self.pos = init_pos.detach().to(torch.float32).clone().contiguous()
         self.v = init_v.detach().to(torch.int32).contiguous().clone()
-        self.shape = shape.detach().to(torch.float32).reshape(B, -1, 3).contiguous()
+        self.shape = shape.detach().to(torch.float32).reshape(B, -1, 3).contiguous() if B else torch.zeros(0, 32, 3, device=dev)
         self.t = torch.full((max(B, 1),), T - 1, dtype=torch.int32, device=dev)
         self.pred_pos = torch.empty(N, 3, device=dev)
         self.pred_h = torch.empty(N, H, device=dev)
@@ -251,19 +272,29 @@ class Sampler:
         self.log_post = torch.empty(N, Cn, device=dev) if keep_traj else None
         self.use_graph = use_graph and not callable(noise)
         self.graph = None
+        self._ws = None
         # guidance: dict(cloud=[M,3] float64 device tensor, radius=..., grad_step=..., ratio=0.2, cloud_ptr=None): point-cloud
         # shape guidance of the predicted x0 while t > grad_step ("ShapeMol+g"); the kernel tests t on the device
         self.guidance = guidance
         if keep_traj:
             S = self.num_steps
-            self.traj = {k: torch.empty((S,) + tuple(s), dtype=dt, device=dev) for k, s, dt in (
-                ('pos', (N, 3), torch.float32), ('v', (N,), torch.int32), ('v0', (N, Cn), torch.float32),
-                ('vt', (N, Cn), torch.float32), ('pos_cond', (N, 3), torch.float32), ('v_cond', (N, Cn), torch.float32))}
+            per_step = max(1, N) * (12 + 4 + 2 * 4 * Cn)
+            if traj_chunk is None:      # ~1 GB per ring half
+                traj_chunk = max(1, min(S, (1 << 30) // per_step))
+            self.chunk = int(max(1, min(traj_chunk, max(S, 1))))
+            spec = (('pos', (N, 3), torch.float32), ('v', (N,), torch.int32), ('v0', (N, Cn), torch.float32), ('vt', (N, Cn), torch.float32))
+            self._ring = [{k: torch.empty((self.chunk,) + s, dtype=dt, device=dev) for k, s, dt in spec} for _ in range(2)]
+            self.traj = {k: torch.empty((S,) + s, dtype=dt) for k, s, dt in spec}                      # host
+            self.traj['pos_cond'] = torch.empty((S, N, 3), dtype=torch.float32, device=dev)             # device (reference :645-646)
+            self.traj['v_cond'] = torch.empty((S, N, Cn), dtype=torch.float32, device=dev)
+            self._side = torch.cuda.Stream(device=dev)
 
     def _step_body(self, step):
         e = self.e
-        # from the second step on the step-independent quantities in the engine's workspace are still valid
-        e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v, reuse_static=step > 0)
+        if self.bd.n_atoms == 0:
+            return
+        # from the second step on the step-independent quantities in the workspace are still valid
+        e.forward(self.pos, self.v, self.bd, self.shape, self.t, self.pred_pos, self.pred_h, self.pred_v, reuse_static=step > 0, owner=self)
         if self.guidance is not None:
             gd = self.guidance
             e.guidance(self.bd, self.pred_pos, gd['cloud'], gd['radius'], ratio=gd.get('ratio', 0.2), t_i32=self.t,
@@ -280,27 +311,48 @@ class Sampler:
         e.decrement_t(self.t)
 
     def _record(self, step):
-        tr = self.traj
+        tr, ring = self.traj, self._ring[(step // self.chunk) & 1]
+        i = step % self.chunk
         tr['pos_cond'][step].copy_(self.pred_pos)     # posterior leaves the predictions intact
         tr['v_cond'][step].copy_(self.pred_v)
-        tr['pos'][step].copy_(self.pos)
-        tr['v'][step].copy_(self.v)
-        tr['v0'][step].copy_(self.log_v0)
-        tr['vt'][step].copy_(self.log_post)
+        ring['pos'][i].copy_(self.pos)
+        ring['v'][i].copy_(self.v)
+        ring['v0'][i].copy_(self.log_v0)
+        ring['vt'][i].copy_(self.log_post)
+
+    def _drain(self, c, event):
+        """Chunk c of the ring -> host, on the side stream (runs beside the main stream's next chunk)."""
+        lo = c * self.chunk
+        n = min(self.chunk, self.num_steps - lo)
+        ring = self._ring[c & 1]
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(event)
+            for k in self.HOST_KEYS:
+                self.traj[k][lo:lo + n].copy_(ring[k][:n])      # blocks the host until the bytes have landed
+        self._side.synchronize()
 
     def run(self, progress=None):
         steps = range(self.num_steps)
         if progress is not None:
             steps = progress(steps)
+        pending = None            # (chunk index, event recorded after its last step)
         for s in steps:
-            if not self.use_graph or s == 0:
+            if not self.use_graph or s == 0 or self.bd.n_atoms == 0:
                 self._step_body(s)        # step 0 runs eagerly (it also warms up the kernels)
             else:
                 if self.graph is None:
                     self._capture(s)
                 self.graph.replay()
-            if self.keep_traj:
+            if self.keep_traj and self.bd.n_atoms:
                 self._record(s)           # the trajectory slot depends on the step: outside the graph
+                if (s + 1) % self.chunk == 0 or s + 1 == self.num_steps:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    if pending is not None:
+                        self._drain(*pending)     # the ring half the NEXT chunk will overwrite
+                    pending = (s // self.chunk, ev)
+        if pending is not None:
+            self._drain(*pending)
         return self.pos, self.v
 
     def _capture(self, step):
@@ -317,6 +369,7 @@ class HostStepper:
     def __init__(self, engine, batch_ligand_dev, n_mols, noise='philox', seed=0, use_graph=True):
         m = engine.module
         self.use_graph, self._graph, self._graph_key = use_graph, None, None
+        self._ws = None
         self.e = engine
         self.bd = BatchDesc(batch_ligand_dev, n_mols)
         dev = batch_ligand_dev.device
@@ -339,7 +392,7 @@ class HostStepper:
         self.d_v.copy_(h_v, non_blocking=True)
         self.d_t.copy_(h_t, non_blocking=True)
         self.d_shape.copy_(h_shape, non_blocking=True)
-        self.e.forward(self.d_pos, self.d_v, self.bd, self.d_shape, self.d_t, self.pred_pos, self.pred_h, self.pred_v)
+        self.e.forward(self.d_pos, self.d_v, self.bd, self.d_shape, self.d_t, self.pred_pos, self.pred_h, self.pred_v, owner=self)
         self.e.posterior(self.bd, self.pred_pos, self.pred_v, self.d_t, self.d_pos, self.d_v, seed=self.seed)
         self.h_pos_out.copy_(self.d_pos, non_blocking=True)
         self.h_v_out.copy_(self.d_v, non_blocking=True)

@@ -1,13 +1,18 @@
 """Imports the UNMODIFIED reference modules from /root/reference through the shims in
 tests/golden/_shims.  Only usable in the build container (the GPU box has no /root/reference);
-used by make_golden.py to create the committed fixtures and by optional CPU tests that are
-skipped when the reference tree is absent."""
+used by make_golden.py to create the committed fixtures, by optional CPU tests that are
+skipped when the reference tree is absent, and by bench.py's CPU arm (which finds the staged copy
+oracle/_ref on the GPU box)."""
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('SHAPEMOL_REFERENCE', '/root/reference')
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_shims')
+# the reference checkout (build container) or the files oracle/stage_ref.py staged for the GPU box (oracle/_ref, git-ignored)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..', 'oracle', '_ref')
+REF_ROOT = os.environ.get('SHAPEMOL_REFERENCE', '/root/reference')
+if not os.path.isdir(os.path.join(REF_ROOT, 'models')) and os.path.isdir(os.path.join(_STAGED, 'models')):
+    REF_ROOT = os.path.abspath(_STAGED)
 
 
 def available():

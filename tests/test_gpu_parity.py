@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 FWD_H128 = ['k32_train', 'k32_eval', 'k8_train', 'k8_eval', 'tiny_train']
 REL_FP32 = 1e-3      # north_star tolerance, fp32-parity mode
-REL_BF16 = 3e-2      # plain bf16 operands (stated separately)
+REL_BF16 = 1.2e-2    # plain bf16 operands (stated separately): ~1.5x the measured 2-3e-3 (x0) / 5-8e-3 (logits)
 
 
 def rel_err(a, b):
@@ -245,6 +245,61 @@ def test_trajectory_teacher_forced_and_free_running(cuda_lib):
     assert rel_err(r['pos_traj'][0], fx['pos_traj'][0]) < REL_FP32
     assert rel_err(r['v0_traj'][0], fx['v0_traj'][0]) < 5e-3
     assert rel_err(r['vt_traj'][0], fx['vt_traj'][0]) < 5e-3
+
+
+def test_trajectory_free_running_bf16_mode(cuda_lib):
+    """The throughput mode (plain bf16 on tcgen05) through the public sample_diffusion API with the reference's injected
+    noise: discrete types agree with the fp32 reference trajectory, positions stay within 1e-2 (stated separately from the
+    1e-3 fp32-parity bar)."""
+    fx = load_golden('trajectory.pt')
+    steps = fx['steps']
+    m = build_model(dict(fx, training=True), 'bf16')
+    m.smb_noise = lambda s: (fx['noise_pos'][s].cuda(), fx['noise_u'][s].cuda())
+    r = m.sample_diffusion(init_ligand_pos=fx['pos0'].cuda(), init_ligand_v=fx['v0'].cuda(), batch_ligand=batch_of(fx['sizes']),
+                           ligand_shape=fx['shape'].view(-1, 3).cuda(), num_steps=steps, center_pos_mode='none')
+    agree = float((torch.stack(r['v_traj']) == fx['v_traj']).float().mean())
+    pos_err = max(rel_err(r['pos_traj'][s], fx['pos_traj'][s]) for s in range(steps))
+    print('bf16 free-running over %d steps: type agreement %.4f, max position error %.2e' % (steps, agree, pos_err))
+    assert agree >= 0.97
+    assert pos_err <= 1e-2
+
+
+@pytest.mark.parametrize('k,sizes', [(4, [30, 17, 5, 32, 21]), (3, [20, 31]), (12, [14, 32, 9, 27])])
+def test_bf16_small_k_many_destinations_per_tile(cuda_lib, k, sizes):
+    """Small k with molecules of 17..32 atoms: many destinations share a 128-row tile (the per-tile destination cap).
+    Plain-bf16 tcgen05 path against the fp32-parity family and the oracle on the same seeded inputs."""
+    from oracle import shapemol_oracle as orc
+    fx = load_golden('forward_k32_eval.pt')
+    sd = golden_weights(fx)
+    g = torch.Generator().manual_seed(100 + k)
+    N = sum(sizes)
+    import synth
+    pos = synth.molecule_like_positions(sizes, 77 + k)
+    v = torch.randint(0, 15, (N,), generator=g)
+    shape, t = 0.07 * torch.randn(len(sizes), 32, 3, generator=g), torch.randint(0, 1000, (len(sizes),), generator=g)
+    with torch.no_grad():
+        ex, eh, el = orc.forward(sd, dict(oracle_cfg(fx), knn=k), pos, v, orc.mol_ptr_from_sizes(sizes), shape, t, training=False)
+    for precision, tol in (('bf16x3', REL_FP32), ('bf16', REL_BF16)):
+        m, _ = make_dropin(knn=k)
+        m.load_state_dict(sd, strict=False)
+        m = m.cuda().eval()
+        m.smb_precision = precision
+        out = m(pos.cuda(), v.cuda(), batch_of(sizes), shape.cuda(), time_step=t.cuda())
+        errs = (rel_err(out['pred_ligand_pos'], ex), rel_err(out['pred_ligand_h'], eh), rel_err(out['pred_ligand_v'], el))
+        print('k=%d %s' % (k, precision), errs)
+        assert max(errs) < tol, (precision, errs)
+
+
+def test_empty_shard_sampler_is_a_noop(cuda_lib):
+    """A rank whose shard holds no molecule (world > n_mols) must still reach the gather: the Sampler loop is a no-op."""
+    from shapemol_b200.engine import Sampler
+    fx = load_golden('forward_k32_eval.pt')
+    m = build_model(fx, 'bf16', training=False)
+    e = torch.empty
+    s = Sampler(m._engine(), e(0, 3, device='cuda'), e(0, dtype=torch.long, device='cuda'), e(0, dtype=torch.long, device='cuda'),
+                e(0, 32, 3, device='cuda'), num_steps=3, noise='philox', keep_traj=False, n_mols=0)
+    p, v = s.run()
+    assert p.shape == (0, 3) and v.shape == (0,)
 
 
 def test_sampler_graph_equals_eager_and_torch_rng_order(cuda_lib):
