@@ -25,7 +25,7 @@ static void fill_edge_weights(EdgeArgs& e, const void* blob, const EdgeMlpOff& o
   e.w1r = vptr(blob, o.w1r); e.b1 = fptr(blob, o.b1); e.ln_g = fptr(blob, o.ln_g); e.ln_b = fptr(blob, o.ln_b);
   e.w2 = vptr(blob, o.w2); e.b2 = fptr(blob, o.b2);
   e.w1r_u = vptr(blob, o.w1r_u); e.w2_u = vptr(blob, o.w2_u);
-  e.w1r_f = vptr(blob, o.w1r_f); e.w2_f = vptr(blob, o.w2_f); e.beta_f = fptr(blob, o.beta_f);
+  e.w1r_f = vptr(blob, o.w1r_f); e.w2_f = vptr(blob, o.w2_f); e.beta_f = fptr(blob, o.beta_f); e.w2_q = vptr(blob, o.w2_q);
 }
 static void fill_node_weights(NodeArgs& n, const void* blob, const NodeMlpOff& o) {
   n.w1 = vptr(blob, o.w1); n.b1 = fptr(blob, o.b1); n.ln_g = fptr(blob, o.ln_g); n.ln_b = fptr(blob, o.ln_b);

@@ -14,15 +14,17 @@
 //   warp  18/19 MMA   : (18: loader + GEMM1, 19: GEMM2) cp.async of the molecule's bf16 projection tiles (3-slot ring), then
 //                       GEMM1 (SS)  D[128 x 128] = A1 . [W1r ; A-tile ; B-tile]         (K = 96)
 //                       GEMM2       ROLE_K/XV (TS): D = z . W2^T, z from TMEM;  ROLE_V (SS): D^T = W2 . z^T
-//   warps 2-9   group 0 (even tiles), warps 10-17 group 1 (odd tiles): thread = (row, column half)
-//                 LN : D -> LayerNorm -> ReLU -> z (bf16; TMEM columns, or smem for ROLE_V)
-//                 E2 : ROLE_K  <Q_i, .> per head, softmax over the destination's rows, x gate -> alpha
+//   warps 4-11  LN : D -> LayerNorm -> ReLU -> z (bf16; TMEM columns, or smem for ROLE_V); thread = (row, column half)
+//   warps 12-27 E2 groups (tiles round-robin):
+//                      ROLE_K  the attention logits come straight out of GEMM2: the query is folded into the second Linear
+//                              per tile,  logit[e, (d, h)] = z_e . M[:, (d, h)],  M = W2^T blockdiag_h(Q_d)  (built by a small
+//                              extra MMA, converted to a bf16 operand by the conversion group), so a row reads the 16 columns
+//                              of its destination; softmax over the destination's rows, x gate -> alpha
 //                      ROLE_V  sum_j alpha (W2 z + b2), lane = channel, in-thread over the rows
 //                      ROLE_XV alpha w (x_i - x_j) -> VN linear maps -> BatchNorm partial sums
-//               while one group waits for its GEMM2 the other group's LayerNorm keeps the SM busy.
 //
-// TMEM (512 columns): D[3] at 0/128/256 (GEMM2 overwrites GEMM1's accumulator in place), z[2] at
-// 384/448.  alpha travels between the kernels in a tile-strided layout [tile][128 rows][16 heads].
+// TMEM (512 columns): ROLE_K D[2] at 0/128 (GEMM2 overwrites GEMM1's accumulator in place), z[2] at 256/320, the query
+// fold's accumulator at 384.  alpha travels between the kernels tile-strided (smb_layout.h kAlphaTileFloats).
 #include "smb_common.cuh"
 #include "smb_kernels.h"
 #include "smb_tc.cuh"
@@ -62,7 +64,9 @@ constexpr int GRP_THREADS = GRP_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
 
 // mbarriers: A1 ring (2 slots), z buffers (2), D buffers (3)
-enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14, B_E2_DONE = 26, B_AB_FULL = 38, B_D1_FREE = 41, N_BARS = 43 };
+enum { B_A1_FULL = 0, B_A1_FREE = 2, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 14, B_E2_DONE = 26, B_AB_FULL = 38, B_D1_FREE = 41,
+       // ROLE_K query fold: Q operand staged (2 slots), fold accumulator full / read, folded operand M ready
+       B_QB_FULL = 43, B_DM_FULL = 45, B_DM_FREE = 46, B_BM_FULL = 47, N_BARS = 48 };
 // TMEM accumulator rings (512 columns in all):
 //   ROLE_K : 3 x 128 (GEMM2 overwrites GEMM1's accumulator in place) + z[2] x 64
 //   ROLE_V : 4 x 128 in place; z lives in shared memory
@@ -74,7 +78,8 @@ template <int ROLE> struct Ring {
   // register budgets (pool: 7 warpgroups x 72 = 504):  72 + 2 LN + NG E2 + (4 - NG) 24 <= 504
 #ifndef SMB_K_LN
 #define SMB_K_LN 96
-#define SMB_K_E2 96
+#define SMB_K_E2 64
+#define SMB_K_CV 88
 #endif
 #ifndef SMB_V_LN
 #define SMB_V_LN 96
@@ -86,48 +91,55 @@ template <int ROLE> struct Ring {
 #endif
   static constexpr int REGS_LN = ROLE == ROLE_XV ? SMB_XV_LN : ROLE == ROLE_V ? SMB_V_LN : ROLE == ROLE_K ? SMB_K_LN : 96;
   static constexpr int REGS_E2 = ROLE == ROLE_XV ? SMB_XV_E2 : ROLE == ROLE_V ? SMB_V_E2 : ROLE == ROLE_K ? SMB_K_E2 : 96;
-  static_assert(72 + 2 * REGS_LN + NG * REGS_E2 + (4 - NG) * REGS_IDLE <= 504, "register pool");
+  static constexpr int REGS_CV = SMB_K_CV;   // ROLE_K: the conversion group (third E2 warpgroup)
+  static_assert(72 + 2 * REGS_LN + NG * REGS_E2 + (ROLE == ROLE_K ? REGS_CV + REGS_IDLE : (4 - NG) * REGS_IDLE) <= 504, "register pool");
   // D2_FULL / E2_DONE mbarriers are indexed by tile % NB2 (the TMEM buffer by tile % ND2).  A parity wait is only
   // unambiguous if the waiter visits every phase of its barrier: an epilogue group sees tiles g, g + NG, ..., so NB2 must
   // be a multiple of both NG and ND2 (ROLE_K: 3 buffers, 4 groups -> 12 barriers)
-  static constexpr int NB2 = ROLE == ROLE_K ? 6 : (ROLE == ROLE_XV || ROLE == ROLE_GATE) ? 8 : 4;
+  static constexpr int NB2 = ROLE == ROLE_K ? 2 : (ROLE == ROLE_XV || ROLE == ROLE_GATE) ? 8 : 4;
   static constexpr bool SEP = ROLE == ROLE_XV || ROLE == ROLE_GATE;   // ROLE_GATE has no GEMM2 at all
-  static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 3;
+  static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 2;
   static constexpr int ND2 = SEP ? 8 : ND1;
-  static constexpr uint32_t Z_COL = SEP ? 256 : 384;
+  static constexpr uint32_t Z_COL = 256;
+  static constexpr uint32_t DM_COL = 384;   // ROLE_K: accumulator of the query fold, [128 m][8 h + d]
   static constexpr uint32_t D2_COL = SEP ? 384 : 0, D2_STRIDE = SEP ? 16 : 128;
 };
 
 template <int ROLE>
 struct Plan {
-  static constexpr int o_bar = 0;                 // 43 mbarriers
-  static constexpr int o_tmem = 352;
-  static constexpr int o_vec = 384;               // ln_g | ln_b | b2   (3 x 128 floats)
+  static constexpr int o_bar = 0;                 // 48 mbarriers
+  static constexpr int o_tmem = 448;
+  static constexpr int o_vec = 512;               // ln_g | ln_b | b2   (3 x 128 floats)
   static constexpr int o_w1r = o_vec + 1536;      // 8192
-  static constexpr int o_w2 = o_w1r + 8192;
+  static constexpr int o_w2 = o_w1r + 8192;       // second Linear (ROLE_K: its transposed image, EdgeMlpOff::w2_q)
   static constexpr int w2_bytes = ROLE == ROLE_GATE ? 0 : ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
   static constexpr int o_a1 = o_w2 + w2_bytes;    // 2 slots
   static constexpr int o_ab = o_a1 + 2 * A1_BYTES;   // 3 slots
   static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float2[2 buffers][2 halves][128]
   static constexpr int o_z = o_stat + 4096;          // ROLE_V: z^T operand, 2 x 32768
   static constexpr int o_e2 = o_z + (ROLE == ROLE_V ? 2 * TM * H * 2 : 0);
-  // E2 scratch, one per group: two staging slots (ROLE_K: q float[16][128]; ROLE_V: alpha float[128][16];
-  // ROLE_XV: alpha | shape float[96]), then role scratch
-  static constexpr int stage_bytes = ROLE == ROLE_XV ? 8192 + 384 : 8192;
-  // ROLE_K stages q one tile of the group ahead (two slots); the others stage after the group's previous tile
-  static constexpr int n_slots = ROLE == ROLE_K ? 2 : 1;
+  // E2 scratch, one per group.  ROLE_V / ROLE_XV: one staging slot (the tile's alpha block; ROLE_XV: + shape float[96]), then
+  // role scratch.  ROLE_K: logits float[128][17] | gate float[128]
+  static constexpr int alpha_bytes = kAlphaTileFloats * 4;
+  static constexpr int stage_bytes = ROLE == ROLE_K ? 0 : ROLE == ROLE_XV ? alpha_bytes + 384 : alpha_bytes;
   static constexpr int e_stage = 0;
-  static constexpr int e_log = n_slots * stage_bytes;       // ROLE_K logits / ROLE_XV w : float[128][17]
-  static constexpr int e_red = e_log + 8704;          // ROLE_K float2[16][16]
+  static constexpr int e_log = stage_bytes;           // ROLE_K logits / ROLE_XV w : float[128][17]
+  static constexpr int e_ew = e_log + 8704;           // ROLE_K float[128]
   static constexpr int e_rel = e_log + 8704;          // ROLE_XV float4[128]
-  static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[16][16][4]
-  static constexpr int e2_bytes = ROLE == ROLE_K ? e_red + 2048 : ROLE == ROLE_V ? n_slots * stage_bytes : e_o + 4096;
+  static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[8][16][4]
+  static constexpr int e2_bytes = ROLE == ROLE_K ? e_ew + 512 : ROLE == ROLE_V ? stage_bytes : e_o + 2048;
   static constexpr int NGP = ROLE == ROLE_XV ? 4 : 2;
   static constexpr int o_vnw = o_e2 + NGP * e2_bytes;     // ROLE_XV: vn_feat | vn_dir
   static constexpr int o_bn = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);   // ROLE_XV: float[16 E2 warps][32] BatchNorm partial sums
-  static constexpr int total = o_bn + (ROLE == ROLE_XV ? 4 * NG_MAX * 32 * 4 : 0);
+  // ROLE_K: Q operand of the query fold (2 slots x 8 k-steps x [16 (hh, d) rows][16 channels] bf16) and the folded operand M
+  // ([128 m][16 nd (d, h)] bf16, MN-major, column-group stride 2048)
+  static constexpr int QB_BYTES = 8 * 512;
+  static constexpr int o_qb = o_bn + (ROLE == ROLE_XV ? 4 * NG_MAX * 32 * 4 : 0);
+  static constexpr int o_bm = o_qb + (ROLE == ROLE_K ? 2 * QB_BYTES : 0);
+  static constexpr int total = o_bm + (ROLE == ROLE_K ? 2 * NDMAX * 2048 : 0);
   static_assert(total <= 227 * 1024, "shared memory budget");
-  static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0 && e2_bytes % 16 == 0, "alignment");
+  static_assert(N_BARS * 8 <= o_tmem, "mbarrier area");
+  static_assert(o_e2 % 128 == 0 && stage_bytes % 16 == 0 && o_z % 128 == 0 && e2_bytes % 16 == 0 && o_qb % 128 == 0 && o_bm % 128 == 0, "alignment");
 };
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     const uint4* src = reinterpret_cast<const uint4*>(a.w1r_f);
     uint4* dst = reinterpret_cast<uint4*>(s_w1r);
     for (int p = tid; p < 8192 / 16; p += THREADS) dst[p] = src[p];
-    const uint4* s2 = reinterpret_cast<const uint4*>(a.w2_f);
+    const uint4* s2 = reinterpret_cast<const uint4*>(ROLE == ROLE_K ? a.w2_q : a.w2_f);
     uint4* d2 = reinterpret_cast<uint4*>(s_w2);
     for (int p = tid; p < P::w2_bytes / 16; p += THREADS) d2[p] = s2[p];
     if (tid < H) {
@@ -230,6 +242,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     // that no one-hot column of a valid row selects
     uint4* z0 = reinterpret_cast<uint4*>(s_a1);
     for (int p = tid; p < (2 * A1_BYTES + 3 * AB_BYTES) / 16; p += THREADS) z0[p] = make_uint4(0u, 0u, 0u, 0u);
+    if (ROLE == ROLE_K) {   // Q operand: block diagonal, its zero chunks are never written again; M operand: finite everywhere
+      uint4* q0 = reinterpret_cast<uint4*>(smem + P::o_qb);
+      for (int p = tid; p < (2 * P::QB_BYTES + 2 * NDMAX * 2048) / 16; p += THREADS) q0[p] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
   if (tid == 32) {
@@ -245,6 +261,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     }
     for (int b = 0; b < 3; ++b) mbar_init(bar + B_AB_FULL + b, 1);
     for (int b = 0; b < 2; ++b) mbar_init(bar + B_D1_FREE + b, GRP_THREADS);
+    for (int b = 0; b < 2; ++b) mbar_init(bar + B_QB_FULL + b, E2_GRP_THREADS);
+    mbar_init(bar + B_DM_FULL, 1);
+    mbar_init(bar + B_DM_FREE, E2_GRP_THREADS);
+    mbar_init(bar + B_BM_FULL, E2_GRP_THREADS);
     mbar_init_fence();
   }
   fence_async_smem();
@@ -421,8 +441,66 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       SMB_TRACE(3, t, gw == 0 && lane == 0);
       mbar_arrive(bar + B_Z_FULL + zb);
     }
+  } else if (ROLE == ROLE_K && warp >= E2_WARP0 + 8 && warp < E2_WARP0 + 12) {
+    reg_inc<R::REGS_CV>();
+    // =====================================================================================
+    // ROLE_K conversion group (every tile): stages the tile's queries as the block-diagonal B operand of the query fold, then
+    // turns the fold's accumulator  M[m, 8 h + d]  (fp32, TMEM)  into the bf16 B operand of GEMM2,  [K = m][N = 16 d + h].
+    // =====================================================================================
+    const int tg = (warp - E2_WARP0 - 8) * 32 + lane;      // = TMEM lane = input channel m
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    unsigned char* s_qb = smem + P::o_qb;
+    unsigned char* s_bm = smem + P::o_bm;
+    const unsigned char* qimg = reinterpret_cast<const unsigned char*>(a.q);
+    // chunk (h, d) = Q_d[8 h .. 8 h + 7] (bf16, 16 bytes): k-step j = h / 2, row n = (h & 1) * 8 + d, k-group h & 1
+    auto stage_q = [&](int t, const Tile& T) {
+      unsigned char* slot = s_qb + (t & 1) * P::QB_BYTES;
+      for (int p = tg; p < T.nd * kHeads; p += E2_GRP_THREADS) {
+        const int h = p / T.nd, d = p - h * T.nd, row = T.a0 + T.d0 + d;
+        cp_async16(slot + (h >> 1) * 512 + (h & 1) * 384 + d * 16,
+                   qimg + (size_t)(row >> 7) * kQChunkBlockBytes + (size_t)h * 2048 + (row & 127) * 16);
+      }
+    };
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 td_cur = nt > 0 ? __ldg(tiles) : zero4, td_nx = nt > 1 ? __ldg(tiles + 1) : zero4;
+    if (nt > 0) stage_q(0, Tile(td_cur));
+    cp_async_commit();
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      const Tile T(td_cur);
+      td_cur = td_nx;
+      if (t + 2 < nt) td_nx = __ldg(tiles + t + 2);
+      // slot (t + 1) & 1 was last read by the fold of tile t - 1, whose accumulator this group has already consumed
+      if (t + 1 < nt) stage_q(t + 1, Tile(td_cur));
+      cp_async_commit();
+      cp_async_wait<1>();
+      fence_async_smem();
+      mbar_arrive(bar + B_QB_FULL + (t & 1));
+      mbar_wait(bar + B_DM_FULL, t & 1);
+      fence_after_sync();
+#pragma unroll
+      for (int hg = 0; hg < 2; ++hg) {
+        uint32_t v[64];
+        tmem_ld32(lane_addr + R::DM_COL + hg * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(lane_addr + R::DM_COL + hg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        wait_ld();
+        if (hg == 1) { fence_before_sync(); mbar_arrive(bar + B_DM_FREE); }
+        // the single M operand was last read by GEMM2 of tile t - 1
+        if (hg == 0 && t >= 1) mbar_wait(bar + B_D2_FULL + (t - 1) % NB2, ((t - 1) / NB2) & 1);
+#pragma unroll
+        for (int d = 0; d < NDMAX; ++d) {
+          if (d < T.nd)   // column 16 d + 8 hg + i of the operand  <-  accumulator column 8 (8 hg + i) + d
+            *reinterpret_cast<uint4*>(s_bm + (2 * d + hg) * 2048 + tg * 16) =
+                make_uint4(pack_bf16(__uint_as_float(v[d]), __uint_as_float(v[8 + d])), pack_bf16(__uint_as_float(v[16 + d]), __uint_as_float(v[24 + d])),
+                           pack_bf16(__uint_as_float(v[32 + d]), __uint_as_float(v[40 + d])), pack_bf16(__uint_as_float(v[48 + d]), __uint_as_float(v[56 + d])));
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(bar + B_BM_FULL);
+    }
+    cp_async_wait<0>();
   } else if (warp >= E2_WARP0 && (ROLE == ROLE_GATE || ((warp - E2_WARP0) >> 2) >= R::NG)) {
-    // ROLE_GATE ends in the LayerNorm role: no GEMM2, no role epilogue; ROLE_V uses two of the four groups.
+    // ROLE_GATE ends in the LayerNorm role: no GEMM2, no role epilogue; ROLE_K / ROLE_V use two of the four groups.
     // Idle warpgroups give their registers back.
     reg_dec<REGS_IDLE>();
   } else if (warp >= E2_WARP0) {
@@ -436,36 +514,29 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
     unsigned char* es = smem + P::o_e2 + g * P::e2_bytes;
     float* s_log = reinterpret_cast<float*>(es + P::e_log);             // ROLE_K logits, ROLE_XV w
-    float2* s_red = reinterpret_cast<float2*>(es + P::e_red);           // ROLE_K
+    float* s_ew = reinterpret_cast<float*>(es + P::e_ew);               // ROLE_K gate
     float4* s_rel = reinterpret_cast<float4*>(es + P::e_rel);           // ROLE_XV
     float* s_o = reinterpret_cast<float*>(es + P::e_o);                 // ROLE_XV
     float bn_s = 0.f, bn_q = 0.f;   // ROLE_XV: per-warp BatchNorm partial sums (lane & 15 = channel, lanes < 16)
 
-    // what tile `t` needs from global memory, staged one tile (of this group) ahead: q rows / alpha tile / shape
-    // (cp.async, slot (t >> 1) & 1) and this thread's gate value / relative position (registers)
+    // what tile `t` needs from global memory, fetched after the group's previous tile: the tile's alpha block / shape
+    // (cp.async) and this thread's gate value / relative position (registers)
     float pre_ew = 0.f, pre_x = 0.f, pre_y = 0.f, pre_z = 0.f;
     auto stage = [&](int t, const Tile& T) {
-      unsigned char* slot = es + P::e_stage + (P::n_slots == 2 ? (t >> 1) & 1 : 0) * P::stage_bytes;
+      unsigned char* slot = es + P::e_stage;
       const int dl = min(T.dst_of(r), NDMAX - 1), sl = r - dl * T.deg;
       const bool valid = r < T.rows();
       if (ROLE == ROLE_K) {
-        // q arrives in node_tc5_kernel's tile image [128-row block][32 column groups][128 rows][4 floats]
-        float* dst = reinterpret_cast<float*>(slot);
-        // consecutive threads fetch consecutive destinations of one column group: contiguous nd x 16 bytes in the image
-        for (int p = tg; p < T.nd * (H / 4); p += E2_GRP_THREADS) {
-          const int cg = p / T.nd, d = p - cg * T.nd, row = T.a0 + T.d0 + d;
-          cp_async16(dst + (d * 32 + cg) * 4, a.q + (size_t)(row >> 7) * (TM * H) + (size_t)cg * (TM * 4) + (row & 127) * 4);
-        }
         pre_ew = 0.f;
         if (valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
       } else {
-        const float* src = a.alpha_t + (size_t)(t_begin + t) * (TM * kHeads);
+        const float* src = a.alpha_t + (size_t)(t_begin + t) * kAlphaTileFloats;
         float* dst = reinterpret_cast<float*>(slot);
 #pragma unroll
-        for (int p = tg; p < TM * kHeads / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        for (int p = tg; p < kAlphaTileFloats / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
       }
       if (ROLE == ROLE_XV) {
-        if (tg < 2 * kHeads * 3 / 4) cp_async16(slot + TM * kHeads * 4 + tg * 16, a.vn_shape + (size_t)T.mol * (2 * kHeads * 3) + tg * 4);
+        if (tg < 2 * kHeads * 3 / 4) cp_async16(slot + P::alpha_bytes + tg * 16, a.vn_shape + (size_t)T.mol * (2 * kHeads * 3) + tg * 4);
         pre_x = pre_y = pre_z = 0.f;
         if (valid) {
           const int i = T.d0 + dl;
@@ -488,88 +559,84 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
       td_cur = td_nx;
       if (t + 2 * NG < nt) td_nx = __ldg(tiles + t + 2 * NG);
-      if (P::n_slots == 2) {
-        if (t + NG < nt) stage(t + NG, Tile(td_cur));   // the other slot: its readers are behind the trailing barrier
-        cp_async_commit();
-      }
+      if (ROLE == ROLE_K && t + NG < nt) stage(t + NG, Tile(td_cur));   // registers only: the next tile's gate value
       const int b3 = t % ND2, bb = t % NB2;   // TMEM buffer / barrier slot
       const uint32_t dcol = R::D2_COL + (uint32_t)b3 * R::D2_STRIDE;
       const int rows = T.rows();
       const bool valid = r < rows;
       const int dl = min(T.dst_of(r), NDMAX - 1);
-      const unsigned char* slot = es + P::e_stage + (P::n_slots == 2 ? (t >> 1) & 1 : 0) * P::stage_bytes;
-      const float* s_q = reinterpret_cast<const float*>(slot);            // ROLE_K
-      const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV
-      const float* s_vs = reinterpret_cast<const float*>(slot + TM * kHeads * 4);   // ROLE_XV: shape part of the VN maps [feat | dir][16][3]
+      const int SL = (T.deg + 3) & ~3;        // alpha slots per (head, destination)
+      const unsigned char* slot = es + P::e_stage;
+      const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV: [16][nd][SL] | sums [16][8]
+      const float* s_vs = reinterpret_cast<const float*>(slot + P::alpha_bytes);   // ROLE_XV: shape part of the VN maps [feat | dir][16][3]
 
-      if (P::n_slots == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
+      if (ROLE != ROLE_K) cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
       mbar_wait(bar + B_D2_FULL + bb, (t / NB2) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
-      named_sync(bar_id, E2_GRP_THREADS);      // staged q / alpha / shape / rel visible to the group
+      if (ROLE != ROLE_K) named_sync(bar_id, E2_GRP_THREADS);      // staged alpha / shape / rel visible to the group
       if (SMB_DBG(a, 1)) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); named_sync(bar_id, E2_GRP_THREADS); continue; }
 
       if (ROLE == ROLE_K) {
-        float l[16];
-        // b2 shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped
-        const float scale = 0.35355339059327373f * 1.4426950408889634f;   // 1/sqrt(dh) (dh = 8) x log2(e): softmax in base 2
+        // logits of this row: the 16 accumulator columns of its destination (already scaled by log2(e) / sqrt(dh) through q;
+        // the second Linear's bias shifts every logit of (i, head) by the same <Q_i, b2>: softmax-invariant, dropped)
+        {
+          float l[16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v[64];
-          tmem_ld32(lane_addr + dcol + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld32(lane_addr + dcol + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          wait_ld();
-          if (hf == 1) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); }
-          const float4* qrow = reinterpret_cast<const float4*>(s_q + dl * H + hf * 64);
+          for (int hh = 0; hh < 16; ++hh) l[hh] = 0.f;
+          const int r0 = qd * 32;
+          if (r0 < rows) {
+            const int d_lo = T.dst_of(r0), d_hi = T.dst_of(min(r0 + 31, rows - 1));
+            for (int d = d_lo; d <= d_hi; ++d) {     // warp-uniform: the destinations this warp's 32 rows belong to
+              uint32_t v[16];
+              tmem_ld16(lane_addr + dcol + d * 16, v);
+              wait_ld();
+              if (d == dl) {
 #pragma unroll
-          for (int hh = 0; hh < 8; ++hh) {
-            const float4 qa = qrow[2 * hh], qb = qrow[2 * hh + 1];
-            uint64_t acc2 = mul2(pk2u(v[8 * hh], v[8 * hh + 1]), pk2(qa.x, qa.y));
-            acc2 = fma2(pk2u(v[8 * hh + 2], v[8 * hh + 3]), pk2(qa.z, qa.w), acc2);
-            acc2 = fma2(pk2u(v[8 * hh + 4], v[8 * hh + 5]), pk2(qb.x, qb.y), acc2);
-            acc2 = fma2(pk2u(v[8 * hh + 6], v[8 * hh + 7]), pk2(qb.z, qb.w), acc2);
-            const float acc = sum2(acc2);
-            l[hf * 8 + hh] = acc * scale;
-            s_log[r * LS + hf * 8 + hh] = l[hf * 8 + hh];
+                for (int hh = 0; hh < 16; ++hh) l[hh] = __uint_as_float(v[hh]);
+              }
+            }
           }
+          fence_before_sync();
+          mbar_arrive(bar + B_E2_DONE + bb);      // the accumulator may be overwritten by GEMM1 of tile t + 2
+#pragma unroll
+          for (int hh = 0; hh < 16; ++hh) s_log[r * LS + hh] = l[hh];
+          s_ew[r] = ew_r;
         }
         named_sync(bar_id, E2_GRP_THREADS);
-        // per (destination, head): max and 1 / sum exp2 over the destination's rows; 2 threads share a pair,
-        // each holds <= 16 of the <= 31 rows in registers
+        // per (destination, head): softmax over the destination's rows x gate.  Two threads share a pair; each owns 16
+        // consecutive slots, holds them in registers and writes its part of alpha[head][destination][slot] with 16-byte stores
         {
           const int part = tg & 1;
+          float* at = a.alpha_t + (size_t)(t_begin + t) * kAlphaTileFloats;
           for (int pair = tg >> 1; pair < T.nd * kHeads; pair += E2_GRP_THREADS / 2) {
             const int pd = pair >> 4, hd = pair & 15;
-            const float* col = s_log + (pd * T.deg) * LS + hd;
+            const float* col = s_log + (pd * T.deg + 16 * part) * LS + hd;
+            const float* gw = s_ew + pd * T.deg + 16 * part;
+            const int nq = T.deg - 16 * part;      // valid slots of this half (may be <= 0)
             float lv[16];
             float mx = -INFINITY;
 #pragma unroll
             for (int qq = 0; qq < 16; ++qq) {
-              const int q = part + 2 * qq;
-              lv[qq] = q < T.deg ? col[q * LS] : -INFINITY;
+              lv[qq] = qq < nq ? col[qq * LS] : -INFINITY;
               mx = fmaxf(mx, lv[qq]);
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             float se = 0.f;
 #pragma unroll
-            for (int qq = 0; qq < 16; ++qq) se += fast_ex2(lv[qq] - mx);
+            for (int qq = 0; qq < 16; ++qq) { lv[qq] = fast_ex2(lv[qq] - mx); se += lv[qq]; }
             se += __shfl_xor_sync(0xffffffffu, se, 1);
-            if (part == 0) s_red[pair] = make_float2(mx, 1.f / se);
-          }
-        }
-        named_sync(bar_id, E2_GRP_THREADS);
-        {
-          float o[16];
+            const float inv = 1.f / se;
+            float asum = 0.f;
 #pragma unroll
-          for (int hh = 0; hh < 16; ++hh) {
-            const float2 mi = s_red[dl * kHeads + hh];
-            o[hh] = fast_ex2(l[hh] - mi.x) * (mi.y * ew_r);
-          }
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.alpha_t + ((size_t)(t_begin + t) * TM + r) * kHeads);
+            for (int qq = 0; qq < 16; ++qq) { lv[qq] = qq < nq ? lv[qq] * inv * gw[qq] : 0.f; asum += lv[qq]; }
+            asum += __shfl_xor_sync(0xffffffffu, asum, 1);
+            float4* dst = reinterpret_cast<float4*>(at + (hd * T.nd + pd) * SL + 16 * part);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (16 * part + 4 * q4 < SL) dst[q4] = make_float4(lv[4 * q4], lv[4 * q4 + 1], lv[4 * q4 + 2], lv[4 * q4 + 3]);
+            if (part == 0) at[kAlphaSumOff + hd * NDMAX + pd] = asum;
           }
         }
       } else if (ROLE == ROLE_V) {
@@ -579,44 +646,49 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
           a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
         } else {
-          // a destination's deg <= 31 columns are read in power-of-two pieces, so the sum over its rows is a
-          // branch-free in-thread loop
-          const float* al0 = s_al + hq;
+          // a destination's deg <= 31 columns: groups of four (one 16-byte alpha load, two packed FMAs), read in power-of-two
+          // pieces, then the deg % 4 leftovers
+          const int n4 = T.deg >> 2;
           for (int pd = 0; pd < T.nd; ++pd) {
-            const int col = pd * T.deg;
-            const uint32_t ta = lane_addr + dcol + col;
+            const uint32_t ta = lane_addr + dcol + pd * T.deg;
+            const float* al = s_al + (hq * T.nd + pd) * SL;
             uint32_t v16[16], v8[8], v4[4], v2[2], v1[1];
             int o = 0;
-            if (T.deg & 16) { tmem_ld16(ta, v16); o = 16; }
-            if (T.deg & 8) { tmem_ld8(ta + o, v8); o += 8; }
-            if (T.deg & 4) { tmem_ld4(ta + o, v4); o += 4; }
+            if (n4 & 4) { tmem_ld16(ta, v16); o = 16; }
+            if (n4 & 2) { tmem_ld8(ta + o, v8); o += 8; }
+            if (n4 & 1) { tmem_ld4(ta + o, v4); o += 4; }
             if (T.deg & 2) { tmem_ld2(ta + o, v2); o += 2; }
             if (T.deg & 1) tmem_ld1(ta + o, v1);
             wait_ld();
-            const float* al = al0 + col * kHeads;
-            float acc = 0.f, asum = 0.f;
-            if (T.deg & 16) {
+            uint64_t acc2 = 0ull;
+            if (n4 & 4) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v16[q]), acc); asum += w; }
-              al += 16 * kHeads;
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(al + 4 * q);
+                acc2 = fma2(pk2u(v16[4 * q], v16[4 * q + 1]), pk2(w.x, w.y), acc2);
+                acc2 = fma2(pk2u(v16[4 * q + 2], v16[4 * q + 3]), pk2(w.z, w.w), acc2);
+              }
+              al += 16;
             }
-            if (T.deg & 8) {
+            if (n4 & 2) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v8[q]), acc); asum += w; }
-              al += 8 * kHeads;
+              for (int q = 0; q < 2; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(al + 4 * q);
+                acc2 = fma2(pk2u(v8[4 * q], v8[4 * q + 1]), pk2(w.x, w.y), acc2);
+                acc2 = fma2(pk2u(v8[4 * q + 2], v8[4 * q + 3]), pk2(w.z, w.w), acc2);
+              }
+              al += 8;
             }
-            if (T.deg & 4) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v4[q]), acc); asum += w; }
-              al += 4 * kHeads;
+            if (n4 & 1) {
+              const float4 w = *reinterpret_cast<const float4*>(al);
+              acc2 = fma2(pk2u(v4[0], v4[1]), pk2(w.x, w.y), acc2);
+              acc2 = fma2(pk2u(v4[2], v4[3]), pk2(w.z, w.w), acc2);
+              al += 4;
             }
-            if (T.deg & 2) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) { const float w = al[q * kHeads]; acc = fmaf(w, __uint_as_float(v2[q]), acc); asum += w; }
-              al += 2 * kHeads;
-            }
-            if (T.deg & 1) { const float w = al[0]; acc = fmaf(w, __uint_as_float(v1[0]), acc); asum += w; }
-            a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, asum, acc);
+            float acc = sum2(acc2);
+            if (T.deg & 2) { acc = fmaf(al[0], __uint_as_float(v2[0]), acc); acc = fmaf(al[1], __uint_as_float(v2[1]), acc); al += 2; }
+            if (T.deg & 1) acc = fmaf(al[0], __uint_as_float(v1[0]), acc);
+            a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, s_al[kAlphaSumOff + hq * NDMAX + pd], acc);
           }
         }
         fence_before_sync();
@@ -629,15 +701,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           fence_before_sync();
           mbar_arrive(bar + B_E2_DONE + bb);
           if (valid) {
-            const float4* al = reinterpret_cast<const float4*>(s_al + r * kHeads);
+            const float* al = s_al + dl * SL + (r - dl * T.deg);     // + head * nd * SL
+            const int hs = T.nd * SL;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 av = al[q];
-              s_log[r * LS + 4 * q] = av.x * (__uint_as_float(v[4 * q]) + s_b2[4 * q]);
-              s_log[r * LS + 4 * q + 1] = av.y * (__uint_as_float(v[4 * q + 1]) + s_b2[4 * q + 1]);
-              s_log[r * LS + 4 * q + 2] = av.z * (__uint_as_float(v[4 * q + 2]) + s_b2[4 * q + 2]);
-              s_log[r * LS + 4 * q + 3] = av.w * (__uint_as_float(v[4 * q + 3]) + s_b2[4 * q + 3]);
-            }
+            for (int hh = 0; hh < 16; ++hh) s_log[r * LS + hh] = al[hh * hs] * (__uint_as_float(v[hh]) + s_b2[hh]);
           }
         }
         named_sync(bar_id, E2_GRP_THREADS);
@@ -688,8 +755,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
       }
       SMB_TRACE(6, t, tg == 0);
-      named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slots are reused by the group's next tiles
-      if (P::n_slots == 1) {
+      named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slot are reused by the group's next tile
+      if (ROLE != ROLE_K) {
         if (t + NG < nt) stage(t + NG, Tile(td_cur));
         cp_async_commit();
       }
@@ -764,15 +831,45 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     }
   } else if (warp == G2_WARP) {
     // =====================================================================================
-    // GEMM2 issuer
+    // GEMM2 issuer (ROLE_K: also the query fold of the NEXT tile, issued ahead of this tile's GEMM2)
     // =====================================================================================
     constexpr uint32_t IDESC2 = idesc_bf16(ROLE == ROLE_XV ? kHeads : H, false);
     const uint32_t w2_base = smem_u32(s_w2);
+    const uint32_t qb_base = smem_u32(smem + P::o_qb), bm_base = smem_u32(smem + P::o_bm);
+    // M[m, 8 h + d] = sum_{c in head h} W2[c, m] Q_d[c]:  k-step j covers the channels of heads 2 j, 2 j + 1, whose 16
+    // output columns (hh, d) start at 16 j;  A = W2^T [m][c] (K-major), B = block-diagonal Q chunk rows [16][16] (K-major)
+    auto fold = [&](int u) {
+      constexpr uint32_t IDESC_F = idesc_bf16(16, false);
+      const uint32_t qb = qb_base + (u & 1) * P::QB_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mma_ss(tmem + R::DM_COL + 16 * j, smem_desc(w2_base + j * 256, 128, 2048), smem_desc(qb + j * 512, 128, 256), IDESC_F, 0);
+      mma_commit(bar + B_DM_FULL);
+    };
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 td_cur = nt > 0 ? __ldg(tiles) : zero4, td_nx = nt > 1 ? __ldg(tiles + 1) : zero4;
+    if (ROLE == ROLE_K && nt > 0) {
+      mbar_wait(bar + B_QB_FULL, 0);
+      fence_after_sync();
+      if (lane == 0) fold(0);
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int u = 0; u < (ROLE == ROLE_GATE ? 0 : nt); ++u) {
       const int zb = u & 1;
+      const int nd = (td_cur.z >> 16) & 0xff;
+      td_cur = td_nx;
+      if (u + 2 < nt) td_nx = __ldg(tiles + u + 2);
+      if (ROLE == ROLE_K && u + 1 < nt) {
+        mbar_wait(bar + B_QB_FULL + ((u + 1) & 1), ((u + 1) >> 1) & 1);
+        mbar_wait(bar + B_DM_FREE, u & 1);       // the conversion group has read the fold of tile u
+        fence_after_sync();
+        if (lane == 0) fold(u + 1);
+        __syncwarp();
+      }
       mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
       if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + (u - ND2) % NB2, ((u - ND2) / NB2) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
+      if (ROLE == ROLE_K) mbar_wait(bar + B_BM_FULL, u & 1);
       fence_after_sync();
       SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {
@@ -782,6 +879,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
           for (int ks = 0; ks < H / 16; ++ks)
             mma_ss(d, smem_desc(w2_base + ks * 256, 128, 2048), smem_desc(zt + ks * 256, 128, 2048), IDESC2, ks > 0);
+        } else if (ROLE == ROLE_K) {
+          // logits[e, 16 d + h] = z[e, :] . M[:, 16 d + h]:  N = 16 nd, B = M operand [K = m][N] MN-major
+          const uint32_t idk = idesc_bf16(16 * nd, true);
+#pragma unroll
+          for (int ks = 0; ks < H / 16; ++ks)
+            mma_ts(d, tmem + Z_COL + zb * 64 + ks * 8, smem_desc(bm_base + ks * 256, 128, 2048), idk, ks > 0);
         } else {
 #pragma unroll
           for (int ks = 0; ks < H / 16; ++ks)

@@ -53,6 +53,7 @@ EdgeMlpOff carve_edge(Carver& c, const smb_model_dims& d, int n2, bool gate) {
   e.w1r_f = c.take((size_t)32 * H * 2);
   e.w2_f = gate ? c.take(H * 4) : c.take((size_t)n2 * H * 2);   // gate: fp32 vector w2 * |gamma|
   e.beta_f = c.take(H * 4);
+  e.w2_q = (!gate && n2 == H) ? c.take((size_t)H * H * 2) : e.w2_f;
   return e;
 }
 NodeMlpOff carve_node(Carver& c, const smb_model_dims& d, int n1, int k1, int n2, bool folded = false, bool out_tc5 = false) {
@@ -129,8 +130,8 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
   w.deg = c.take(n * 4);
   w.ew = c.take(n * KS * 4);
   w.max_tiles = (int)(n / 4 + b + 8);
-  {  // alpha: [N][k+1][16] (atom-strided kernels) or [tile][128][16] (warp-specialised pipeline)
-    const size_t by_atom = n * KS * kHeads * 4, by_tile = (size_t)w.max_tiles * 128 * kHeads * 4;
+  {  // alpha: [N][k+1][16] (atom-strided kernels) or [tile][kAlphaTileFloats] (warp-specialised pipeline)
+    const size_t by_atom = n * KS * kHeads * 4, by_tile = (size_t)w.max_tiles * kAlphaTileFloats * 4;
     w.alpha = c.take(by_atom > by_tile ? by_atom : by_tile);
   }
   w.x = c.take(n * 3 * 4);
@@ -334,6 +335,12 @@ static int pack_impl(const smb_model_dims& d, const float* const* hp, uint8_t* b
       for (int n = 0; n < n2; ++n)
         for (int k = 0; k < H; ++k)
           f2[((size_t)(n / 8) * 2048 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] = f2bf(w2[(size_t)n * H + k] * fo.mag[k]);
+      if (n2 == H) {   // transposed image for the query fold: row = input channel m, k = output channel c
+        uint16_t* fq = reinterpret_cast<uint16_t*>(blob + e.w2_q);
+        for (int m = 0; m < H; ++m)
+          for (int c = 0; c < H; ++c)
+            fq[((size_t)(m / 8) * 2048 + (size_t)(c / 8) * 128 + (m % 8) * 16 + (c % 8) * 2) / 2] = f2bf(w2[(size_t)c * H + m] * fo.mag[m]);
+      }
       put(blob, e.beta_f, fo.beta.data(), H);
     }
   };

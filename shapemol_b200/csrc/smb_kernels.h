@@ -109,7 +109,7 @@ struct EdgeArgs {
   const int* deg;          // [N]
   const float* ab;         // [N][4H]; columns [col_a, col_a+H) = dst part, [col_b, col_b+H) = src part
   int col_a, col_b;
-  const float* q;          // [N][H]           (ROLE_K)
+  const float* q;          // [N][H] fp32 (mma.sync kernels) / bf16 chunk image, pre-scaled (warp-specialised pipeline)   (ROLE_K)
   const float* ew_in;      // [N][k+1]         (ROLE_K: folded into alpha)
   float* ew_out;           // [N][k+1]         (ROLE_GATE)
   float* alpha;            // [N][k+1][16]     (ROLE_K out; ROLE_V / ROLE_XV in)
@@ -124,11 +124,12 @@ struct EdgeArgs {
   const void* w1r; const float* b1; const float *ln_g, *ln_b; const void* w2; const float* b2;
   const void* w1r_u; const void* w2_u;   // tcgen05 operand images (EdgeMlpOff::w1r_u / w2_u)
   const void* w1r_f; const void* w2_f; const float* beta_f;   // LayerNorm-folded images (EdgeMlpOff::w1r_f / w2_f / beta_f)
+  const void* w2_q;        // EdgeMlpOff::w2_q (ROLE_K of the warp-specialised pipeline)
   // warp-specialised pipeline (smb_edge_ws.cu)
   const void* abh;         // bf16 node projections in per-molecule operand layout (node_mlp_kernel out1_h)
   const int4* tiles;       // static tile list (build_tiles_kernel)
   const int* n_tiles;
-  float* alpha_t;          // [tile][128 rows][16 heads]  (ROLE_K out; ROLE_V / ROLE_XV in)
+  float* alpha_t;          // [tile][kAlphaTileFloats]: [16 heads][nd][SL] + sums  (ROLE_K out; ROLE_V / ROLE_XV in)
   int dbg;                 // SMB_WS_DBG bit mask (timing experiments only: results are wrong when set)
 };
 // bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes

@@ -35,6 +35,9 @@ struct EdgeMlpOff {
   size_t w1r_f;  // as w1r_u
   size_t w2_f;   // as w2_u
   size_t beta_f; // [H] fp32
+  // hk / xk only: the folded second Linear TRANSPOSED, [H m][H c] K-major (byte(m, c) as w2_u with n = m, k = c): A operand of
+  // the per-tile query fold  M[m, (d, h)] = sum_{c in head h} W2[c, m] Q_d[c]  (ROLE_K of smb_edge_ws.cu)
+  size_t w2_q;
 };
 
 // Node-level chain: Y1 = X W1^T + b1 ; first n_pass columns are written out as they are, the last H
@@ -58,8 +61,16 @@ struct NodeMlpOff {
   size_t w2_t;   // [128 n][128 k] K-major (as EdgeMlpOff::w2_u), k-columns multiplied by |gamma|
   size_t beta_t; // [H] beta / |gamma|
 };
-// q of the tcgen05 node kernel (bf16 mode): tile image, float offset of (row r, column c) =
-//   (r / 128) * 128 * 128 + (c / 4) * 128 * 4 + (r % 128) * 4 + c % 4     (the workspace slot is sized for whole 128-row blocks)
+// h of the tcgen05 node kernels between layers (bf16 mode): tile image, float offset of (row r, column c) =
+//   (r / 128) * 128 * 128 + (c / 4) * 128 * 4 + (r % 128) * 4 + c % 4     (the workspace slots are sized for whole 128-row blocks)
+// q of the tcgen05 node kernel: bf16, pre-multiplied by log2(e) / sqrt(head_dim), as a chunk image -- one 16-byte chunk per
+// (row, head):  byte offset of (row r, head h) = (r / 128) * 32768 + h * 2048 + (r % 128) * 16   (8 channels of the head)
+constexpr int kQChunkBlockBytes = 128 * 128 * 2;
+// alpha (softmax x gate) of the warp-specialised edge pipeline, per tile: [16 heads][nd destinations][SL slots] fp32 with
+// SL = deg rounded up to 4 (slots >= deg are zero), then sum_j alpha per (head, destination) at float kAlphaSumOff + h * 8 + d.
+// nd * SL <= 144 for nd <= 8, nd * deg <= 128.
+constexpr int kAlphaSumOff = 16 * 144;
+constexpr int kAlphaTileFloats = kAlphaSumOff + 16 * 8;   // 2432 floats = 9728 bytes per tile
 constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
 constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
 constexpr int kNodeOutKx = 272;                         // node_output: 128 (agg) + 128 (h) + 16 (bias hi | bias lo | zeros)

@@ -277,23 +277,40 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
           fence_before_sync();
           mbar_arrive(bar + B_Z_FULL);
         } else if (s == G2_STEP) {
-          if (valid && !SMB_DBG(a, 2)) {
-            // MODE 0: q goes out in the tile image [128-row block][32 column groups][128 rows][4 floats] (kQImage in smb_layout.h): a
-            // warp's 32 rows store 512 contiguous bytes per column group instead of 32 scattered 16-byte pieces; the K edge role
-            // gathers its destinations' rows from it with 16-byte cp.async pieces.  MODE 1: h' stays row-major [N][128].
-            const bool oi = MODE == 0 || a.out2_image;
+          if (MODE == 0) {
+            // q goes out as bf16, pre-multiplied by log2(e) / sqrt(head_dim) (the K edge role's softmax works in base 2), in the
+            // chunk image [128-row block][16 heads][128 rows][16 bytes] (smb_layout.h): a warp's 32 rows store 512 contiguous
+            // bytes per head, and the K role cp.asyncs one 16-byte chunk per (destination, head) straight into its MMA operand
+            if (valid && !SMB_DBG(a, 2)) {
+              constexpr float qs = 0.35355339059327373f * 1.4426950408889634f;
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.out2) + (size_t)tile * kQChunkBlockBytes +
+                                                    (size_t)(half * 8) * 2048 + r * 16);
+#pragma unroll
+              for (int hd = 0; hd < 8; ++hd) {
+                const float4 b0 = *reinterpret_cast<const float4*>(s_b2 + half * 64 + hd * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_b2 + half * 64 + hd * 8 + 4);
+                const int e = hd * 8;
+                dst[hd * 128] = make_uint4(pack_bf16((__uint_as_float(v[e]) + b0.x) * qs, (__uint_as_float(v[e + 1]) + b0.y) * qs),
+                                           pack_bf16((__uint_as_float(v[e + 2]) + b0.z) * qs, (__uint_as_float(v[e + 3]) + b0.w) * qs),
+                                           pack_bf16((__uint_as_float(v[e + 4]) + b1.x) * qs, (__uint_as_float(v[e + 5]) + b1.y) * qs),
+                                           pack_bf16((__uint_as_float(v[e + 6]) + b1.z) * qs, (__uint_as_float(v[e + 7]) + b1.w) * qs));
+              }
+            }
+          } else if (valid && !SMB_DBG(a, 2)) {
+            // h' : row-major [N][128] or the tile image [128-row block][32 column groups][128 rows][4 floats] between layers
+            const bool oi = a.out2_image;
             float4* dst = oi ? reinterpret_cast<float4*>(a.out2 + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
                              : reinterpret_cast<float4*>(a.out2 + (size_t)grow * H + half * 64);
             const int DSTEP = oi ? TM : 1;   // float4 stride between consecutive column groups
-            const bool ri = MODE == 1 && a.xb_image;   // the residual is the h operand (same layout)
-            const float4* res = MODE != 1 ? nullptr
-                                : ri ? reinterpret_cast<const float4*>(a.residual + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
-                                     : reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64);
+            const bool ri = a.xb_image;      // the residual is the h operand (same layout)
+            const float4* res = ri ? reinterpret_cast<const float4*>(a.residual + (size_t)tile * (TM * H) + (size_t)(half * 16) * (TM * 4) + r * 4)
+                                   : reinterpret_cast<const float4*>(a.residual + (size_t)grow * H + half * 64);
             const int RSTEP = ri ? TM : 1;
 #pragma unroll
             for (int e = 0; e < 64; e += 4) {
               float4 bb = *reinterpret_cast<const float4*>(s_b2 + half * 64 + e);
-              if (MODE == 1) { const float4 rv = __ldg(res + (e / 4) * RSTEP); bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w; }
+              const float4 rv = __ldg(res + (e / 4) * RSTEP);
+              bb.x += rv.x; bb.y += rv.y; bb.z += rv.z; bb.w += rv.w;
               dst[(e / 4) * DSTEP] = make_float4(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y, __uint_as_float(v[e + 2]) + bb.z,
                                        __uint_as_float(v[e + 3]) + bb.w);
             }
@@ -321,10 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc5_kernel(NodeArgs a) {
 }  // namespace
 
 bool node_tc5_supported(const smb_model_dims& d, int n_max) {
-#ifdef SMB_DEBUG
-  static const bool off = getenv("SMB_NODE_LEGACY") != nullptr;   // debugging aid: mma.sync node kernels in bf16 mode
-  if (off) return false;
-#endif
+  // always together with the warp-specialised edge pipeline: q travels between them as a pre-scaled bf16 chunk image
   return edge_ws_supported(d, n_max);
 }
 
