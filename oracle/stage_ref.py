@@ -18,6 +18,8 @@ FILES = [
     'models/shape_vn_layers.py', 'models/shape_pointcloud_modelAE.py',
     'config/training/dgcnn_signeddist_512_attention_residue_uniform_pos0_10_pos1.e-7_0.01_6_v001.yml',
     'trained_models/se_model.pt',
+    # the caller of the hot path: tests/test_gpu_script_contract.py executes its sample_diffusion_ligand() unmodified against the drop-in
+    'scripts/sample_diffusion.py',
 ]
 
 

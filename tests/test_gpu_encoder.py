@@ -128,3 +128,37 @@ def test_encoder_argument_errors(cuda_lib):
     with pytest.raises(ValueError):
         ae.encoder(torch.zeros(1, 64, 3, device='cuda'))
     assert ae.encoder(torch.zeros(0, 1, 64, 3, device='cuda')).shape == (0, 32, 3)
+
+
+def test_frontend_many_shapes_end_to_end(cuda_lib):
+    """molecules -> mesh-free surface clouds -> centred / bounded / batched -> CUDA encoder, through
+    shapemol_b200.shape_frontend.get_pointAE_shape_emb (reference utils/shape.py:240-284).  The latents of every batch are
+    checked against the oracle encoder evaluated on exactly the clouds the front end produced."""
+    import synth
+    from oracle import shapemol_oracle as orc
+    from shapemol_b200 import shape_frontend as sf
+    fx = load_golden('encoder.pt')
+    ae = make_ae(fx, True)
+    g = torch.Generator(device='cuda').manual_seed(9)
+    sizes = [13, 27, 9, 21, 18]
+    xyz = synth.molecule_like_positions(sizes, 31)
+    mols, o = [], 0
+    for n in sizes:
+        mols.append(dict(coords=xyz[o:o + n].cuda(), atomic_numbers=[6, 7, 8][o % 3:o % 3 + 1] * n))
+        o += n
+    zs, bounds, clouds, centers = sf.get_pointAE_shape_emb(mols, ae, 256, batch_size=2, generator=g)
+    assert zs.shape == (5, 32, 3) and bounds.shape == (5, 3, 2) and centers.shape == (5, 3)
+    assert [tuple(c.shape) for c in clouds] == [(2, 1, 256, 3), (2, 1, 256, 3), (1, 1, 256, 3)]
+    assert all(float(c.mean(dim=2).abs().max()) < 1e-4 for c in clouds)            # centred
+    assert bool((bounds[:, :, 0] < 0).all() and (bounds[:, :, 1] > 0).all())       # the box contains the centre
+    w = oracle_weights(fx)
+    w64 = {k: (v.double() if v.is_floating_point() else v) for k, v in w.items()}
+    o = 0
+    for c in clouds:
+        with torch.no_grad():
+            ref = orc.encoder_forward(w, c, k=fx['num_k'], training=True)
+            ref64 = orc.encoder_forward(w64, c.double(), k=fx['num_k'], training=True)
+        e, e64 = rel_err(zs[o:o + c.shape[0]], ref), rel_err(zs[o:o + c.shape[0]], ref64)
+        print('front end batch of %d: rel err %.2e (fp32 oracle) %.2e (fp64 oracle)' % (c.shape[0], e, e64))
+        assert min(e, e64) < REL and e < 5e-3
+        o += c.shape[0]
