@@ -14,6 +14,7 @@ DST = os.path.join(HERE, '_ref')
 
 # the six hot-path modules, the training YAML the constructor reads, the shipped shape-encoder checkpoint
 FILES = [
+    'models/__init__.py',            # (empty) makes `models` a regular package, like in the checkout
     'models/molopt_score_model.py', 'models/uni_transformer.py', 'models/common.py', 'models/diffusion.py',
     'models/shape_vn_layers.py', 'models/shape_pointcloud_modelAE.py',
     'config/training/dgcnn_signeddist_512_attention_residue_uniform_pos0_10_pos1.e-7_0.01_6_v001.yml',

@@ -79,7 +79,8 @@ enum { B_A1_FULL = 0, B_Z_FULL = 4, B_D1_FULL = 6, B_D2_FULL = 18, B_E2_DONE = 3
        B_QB_FULL = 47, B_DM_FULL = 49, B_DM_FREE = 50, B_BM_FULL = 51, N_BARS = 52 };
 // TMEM accumulator rings (512 columns in all):
 //   ROLE_K : 3 x 128 (GEMM2 overwrites GEMM1's accumulator in place) + z[2] x 64
-//   ROLE_V : 4 x 128 in place; z lives in shared memory
+//   ROLE_V : 3 x 128 in place (+ 128 spare columns: the epilogue reads 32 columns per destination whatever its degree);
+//            z lives in shared memory
 //   ROLE_XV: GEMM2 has 16 output columns, so it gets its own ring: D1 2 x 128 | z[2] x 64 | D2 8 x 16.  D1 is free again as
 //            soon as the LayerNorm has read it, and a late epilogue no longer stalls GEMM1.
 template <int ROLE> struct Ring {
@@ -114,9 +115,9 @@ template <int ROLE> struct Ring {
   // D2_FULL / E2_DONE mbarriers are indexed by tile % NB2 (the TMEM buffer by tile % ND2).  A parity wait is only
   // unambiguous if the waiter visits every phase of its barrier: an epilogue group sees tiles g, g + NG, ..., so NB2 must
   // be a multiple of both NG and ND2 (ROLE_K: 3 buffers, 4 groups -> 12 barriers)
-  static constexpr int NB2 = ROLE == ROLE_K ? 2 : (ROLE == ROLE_XV || ROLE == ROLE_GATE) ? 8 : 4;
+  static constexpr int NB2 = ROLE == ROLE_K ? 2 : (ROLE == ROLE_XV || ROLE == ROLE_GATE) ? 8 : 6;
   static constexpr bool SEP = ROLE == ROLE_XV || ROLE == ROLE_GATE;   // ROLE_GATE has no GEMM2 at all
-  static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 4 : 2;
+  static constexpr int ND1 = SEP ? 2 : ROLE == ROLE_V ? 3 : 2;   // ROLE_V: 3 x 128 + 128 spare columns that its 32-column reads may run into
   static constexpr int ND2 = SEP ? 8 : ND1;
   static constexpr uint32_t Z_COL = 256;
   static constexpr uint32_t DM_COL = 384;   // ROLE_K: accumulator of the query fold, [128 m][8 h + d]
@@ -291,6 +292,17 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  if (ROLE == ROLE_V && warp < 4) {
+    // the ROLE_V epilogue reads up to 3 columns past a tile's last row (zero alpha weights): they must hold finite values from
+    // the start, in the accumulators not yet written and in the spare columns behind the ring
+    uint32_t zr[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) zr[q] = 0u;
+    for (int c0 = 0; c0 < (int)TMEM_COLS; c0 += 32) tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + c0, zr);
+    wait_st();
+    fence_before_sync();
+  }
+  if (ROLE == ROLE_V) { __syncthreads(); fence_after_sync(); }
 
   // projection tiles of tile t's molecule: two bulk copies (dst part | src part, n * 256 bytes each) into slot t % 3, in the
   // MN-major operand layout with an n * 16-byte column-group stride (written like that by node_tc5_kernel); one thread
@@ -706,49 +718,31 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
           a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
         } else {
-          // a destination's deg <= 31 columns: groups of four (one 16-byte alpha load, two packed FMAs), read in power-of-two
-          // pieces, then the deg % 4 leftovers
-          const int n4 = T.deg >> 2;
-          for (int pd = 0; pd < T.nd; ++pd) {
-            const uint32_t ta = lane_addr + dcol + pd * T.deg;
+          // a destination's deg <= 31 columns are read as ONE 32-column load (16 when deg <= 16) -- whatever follows them, the
+          // next destination's columns or the spare TMEM columns behind the ring, is multiplied by the zero padding of its
+          // alpha slots (SL = deg rounded up to 4) or not used at all -- and two destinations share one tcgen05.wait::ld:
+          // the load latency is paid nd / 2 times per tile.  Groups of four slots: one 16-byte alpha load, two packed FMAs.
+          const int n4 = SL >> 2;
+          auto reduce32 = [&](int pd, const uint32_t (&v)[32]) {
             const float* al = s_al + (hq * T.nd + pd) * SL;
-            uint32_t v16[16], v8[8], v4[4], v2[2], v1[1];
-            int o = 0;
-            if (n4 & 4) { tmem_ld16(ta, v16); o = 16; }
-            if (n4 & 2) { tmem_ld8(ta + o, v8); o += 8; }
-            if (n4 & 1) { tmem_ld4(ta + o, v4); o += 4; }
-            if (T.deg & 2) { tmem_ld2(ta + o, v2); o += 2; }
-            if (T.deg & 1) tmem_ld1(ta + o, v1);
-            wait_ld();
             uint64_t acc2 = 0ull;
-            if (n4 & 4) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q)
+              if (q < n4) {
                 const float4 w = *reinterpret_cast<const float4*>(al + 4 * q);
-                acc2 = fma2(pk2u(v16[4 * q], v16[4 * q + 1]), pk2(w.x, w.y), acc2);
-                acc2 = fma2(pk2u(v16[4 * q + 2], v16[4 * q + 3]), pk2(w.z, w.w), acc2);
+                acc2 = fma2(pk2u(v[4 * q], v[4 * q + 1]), pk2(w.x, w.y), acc2);
+                acc2 = fma2(pk2u(v[4 * q + 2], v[4 * q + 3]), pk2(w.z, w.w), acc2);
               }
-              al += 16;
-            }
-            if (n4 & 2) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(al + 4 * q);
-                acc2 = fma2(pk2u(v8[4 * q], v8[4 * q + 1]), pk2(w.x, w.y), acc2);
-                acc2 = fma2(pk2u(v8[4 * q + 2], v8[4 * q + 3]), pk2(w.z, w.w), acc2);
-              }
-              al += 8;
-            }
-            if (n4 & 1) {
-              const float4 w = *reinterpret_cast<const float4*>(al);
-              acc2 = fma2(pk2u(v4[0], v4[1]), pk2(w.x, w.y), acc2);
-              acc2 = fma2(pk2u(v4[2], v4[3]), pk2(w.z, w.w), acc2);
-              al += 4;
-            }
-            float acc = sum2(acc2);
-            if (T.deg & 2) { acc = fmaf(al[0], __uint_as_float(v2[0]), acc); acc = fmaf(al[1], __uint_as_float(v2[1]), acc); al += 2; }
-            if (T.deg & 1) acc = fmaf(al[0], __uint_as_float(v1[0]), acc);
-            a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, s_al[kAlphaSumOff + hq * NDMAX + pd], acc);
+            a.agg[(size_t)(T.a0 + T.d0 + pd) * H + c] = fmaf(b2c, s_al[kAlphaSumOff + hq * NDMAX + pd], sum2(acc2));
+          };
+          for (int pd = 0; pd < T.nd; pd += 2) {
+            uint32_t va[32], vb[32];
+            const bool two = pd + 1 < T.nd;
+            tmem_ld32(lane_addr + dcol + pd * T.deg, va);
+            if (two) tmem_ld32(lane_addr + dcol + (pd + 1) * T.deg, vb);
+            wait_ld();
+            reduce32(pd, va);
+            if (two) reduce32(pd + 1, vb);
           }
         }
         fence_before_sync();
