@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libshapemol_b200.so')
-SOURCES = ['smb_host.cu', 'smb_api.cu', 'smb_small_kernels.cu', 'smb_node_mlp.cu', 'smb_node_tc5.cu', 'smb_edge_attn.cu', 'smb_edge_ws.cu', 'smb_generic.cu', 'smb_encoder.cu']
+SOURCES = ['smb_host.cu', 'smb_api.cu', 'smb_small_kernels.cu', 'smb_node_mlp.cu', 'smb_node_tc5.cu', 'smb_edge_attn.cu', 'smb_edge_ws.cu', 'smb_generic.cu', 'smb_encoder.cu', 'smb_tc_gemm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

@@ -842,12 +842,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (t + 2 < nt) n_nx = __ldg(tiles + t + 2).z & 0xff;
       const int4 td_l = td_ld;
       if (ROLE == ROLE_XV && t + 3 < nt) td_ld = __ldg(tiles + t + 3);
-      mbar_wait(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
+      mbar_wait<32>(bar + B_A1_FULL + (t & 1), (t >> 1) & 1);
       SMB_TRACE(7, t, lane == 0);
-      if (R::SEP) { if (t >= ND1) mbar_wait(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
-      else if (t >= ND1) mbar_wait(bar + B_E2_DONE + (t - ND1) % NB2, ((t - ND1) / NB2) & 1);   // tile t - ND1 left D[t % ND1]
+      if (R::SEP) { if (t >= ND1) mbar_wait<32>(bar + B_D1_FREE + t % ND1, (t / ND1 - 1) & 1); }   // LayerNorm(t - ND1) has read D1[t % ND1]
+      else if (t >= ND1) mbar_wait<32>(bar + B_E2_DONE + (t - ND1) % NB2, ((t - ND1) / NB2) & 1);   // tile t - ND1 left D[t % ND1]
       SMB_TRACE(12, t, lane == 0);
-      if (ROLE != ROLE_GATE) mbar_wait(bar + B_AB_FULL + t % 3, (t / 3) & 1);
+      if (ROLE != ROLE_GATE) mbar_wait<32>(bar + B_AB_FULL + t % 3, (t / 3) & 1);
       fence_after_sync();
       SMB_TRACE(1, t, lane == 0);
       if (lane == 0) {
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       }
       __syncwarp();
       if (ROLE == ROLE_XV) {   // projection slot (t + 2) % 3 was read by GEMM1(t - 1)
-        if (t >= 1) mbar_wait(bar + B_D1_FULL + (t - 1) % NB1, ((t - 1) / NB1) & 1);
+        if (t >= 1) mbar_wait<32>(bar + B_D1_FULL + (t - 1) % NB1, ((t - 1) / NB1) & 1);
         if (lane == 0) load_ab(t + 2, td_l);
       }
     }
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         const int4 td_ld = td_nx;
         if (t + 3 < nt) td_nx = __ldg(tiles + t + 3);
         // projection slot (t + 2) % 3 was read by GEMM1(t - 1)
-        if (t >= 1) mbar_wait(bar + B_D1_FULL + (t - 1) % NB1, ((t - 1) / NB1) & 1);
+        if (t >= 1) mbar_wait<32>(bar + B_D1_FULL + (t - 1) % NB1, ((t - 1) / NB1) & 1);
         SMB_TRACE(10, t, true);
         load_ab(t + 2, td_ld);
         SMB_TRACE(11, t, true);
@@ -903,8 +903,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     const uint32_t w2_base = smem_u32(s_w2), qb_base = smem_u32(smem + P::o_qb);
 #pragma unroll 1
     for (int u = 0; u < nt; ++u) {
-      mbar_wait(bar + B_QB_FULL + (u & 1), (u >> 1) & 1);
-      if (u >= 1) mbar_wait(bar + B_DM_FREE, (u - 1) & 1);       // the conversion group has read the fold of tile u - 1
+      mbar_wait<32>(bar + B_QB_FULL + (u & 1), (u >> 1) & 1);
+      if (u >= 1) mbar_wait<32>(bar + B_DM_FREE, (u - 1) & 1);       // the conversion group has read the fold of tile u - 1
       fence_after_sync();
       SMB_TRACE(18, u, lane == 0);
       if (lane == 0) {
@@ -931,9 +931,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const int nd = (td_cur.z >> 16) & 0xff;
       td_cur = td_nx;
       if (u + 2 < nt) td_nx = __ldg(tiles + u + 2);
-      mbar_wait(bar + B_Z_FULL + zb, (u >> 1) & 1);
-      if (R::SEP && u >= ND2) mbar_wait(bar + B_E2_DONE + (u - ND2) % NB2, ((u - ND2) / NB2) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
-      if (ROLE == ROLE_K) mbar_wait(bar + B_BM_FULL, u & 1);
+      mbar_wait<32>(bar + B_Z_FULL + zb, (u >> 1) & 1);
+      if (R::SEP && u >= ND2) mbar_wait<32>(bar + B_E2_DONE + (u - ND2) % NB2, ((u - ND2) / NB2) & 1);   // epilogue(u - ND2) has read D2[u % ND2]
+      if (ROLE == ROLE_K) mbar_wait<32>(bar + B_BM_FULL, u & 1);
       fence_after_sync();
       SMB_TRACE(4, u, lane == 0);
       if (lane == 0) {

@@ -1,10 +1,11 @@
 // Generic-shape path (hidden_dim != 128, e.g. the 256-wide / k = 48 / 60-atom stress configuration of BASELINE
 // configs[4]): the reference formulation of one network evaluation (models/molopt_score_model.py:286-320,
 // models/uni_transformer.py:48-162,289-333,475-540) evaluated literally in fp32 with small dedicated kernels -- a gathered
-// SGEMM for every Linear, row-wise LayerNorm / activation, and per-destination attention kernels over the dense [N, k+1]
-// neighbour table.  No tensor cores, no fusion: this path exists so that every supported configuration has a CUDA
-// implementation whose results match the reference to fp32 round-off; the tuned kernels (smb_edge_ws.cu, smb_node_tc5.cu,
-// smb_edge_attn.cu) cover hidden 128.  Weights are read from the raw fp32 copy at the end of the packed blob
+// tcgen05 GEMM (split-bf16 products, smb_tc_gemm.cu) for every Linear -- the edge-MLP input kv = [r | h_dst | h_src | inv] is one
+// concatenated gathered operand --, row-wise LayerNorm / activation, and per-destination attention kernels over the dense
+// [N, k+1] neighbour table.  No fusion across the MLP: this path exists so that every supported configuration has a CUDA
+// implementation whose results match the reference at the fp32-parity level; the fused kernels (smb_edge_ws.cu,
+// smb_node_tc5.cu, smb_edge_attn.cu) cover hidden 128.  Weights are read from the raw fp32 copy at the end of the packed blob
 // (ModelLayout::raw, in smb_param_name order).
 #include <map>
 #include <mutex>
@@ -15,61 +16,6 @@
 namespace smb {
 
 namespace {
-
-// ---- C[M x N] (+)= A[rows gathered by a_idx][K] . W[N][K]^T (+ bias) ------------------------------------------------
-constexpr int TS = 64, TK = 16;
-__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const int* __restrict__ a_idx, int lda,
-                                                    const float* __restrict__ W, int ldw, int M, int N, int K,
-                                                    const float* __restrict__ bias, int accumulate, float* __restrict__ C, int ldc) {
-  __shared__ float As[TK][TS + 1], Ws[TK][TS + 1];
-  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += TK) {
-    for (int p = threadIdx.x; p < TS * TK; p += 256) {
-      const int r = p / TK, kk = p % TK;
-      const int m = m0 + r, k = k0 + kk;
-      float av = 0.f, wv = 0.f;
-      if (m < M && k < K) {
-        const int row = a_idx ? a_idx[m] : m;
-        if (row >= 0) av = A[(size_t)row * lda + k];
-      }
-      const int n = n0 + r;
-      if (n < N && k < K) wv = W[(size_t)n * ldw + k];
-      As[kk][r] = av;
-      Ws[kk][r] = wv;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < TK; ++kk) {
-      float a4[4], w4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a4[i] = As[kk][ty * 4 + i]; w4[i] = Ws[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= N) continue;
-      float v = acc[i][j] + (bias ? bias[n] : 0.f);
-      if (accumulate) v += C[(size_t)m * ldc + n];
-      C[(size_t)m * ldc + n] = v;
-    }
-  }
-}
 
 // ---- row-wise LayerNorm(eps 1e-5, affine) + ReLU (models/common.py:50-64), or shifted softplus (:39-45): one warp per row --
 __global__ void __launch_bounds__(128) row_act_kernel(float* __restrict__ X, int M, int Hd, const float* __restrict__ gamma,
@@ -223,12 +169,24 @@ __global__ void __launch_bounds__(128) xv_vn_kernel(const float* __restrict__ al
   }
 }
 
+// C[M x N] (+)= A[rows gathered by a_idx][K] . W[N][K]^T (+ bias): the tcgen05 split-bf16 GEMM (smb_tc_gemm.cu)
+struct Seg { const float* a; const int* idx; int lda; int k; };
+int gemm_cat(const Seg* segs, int n_segs, const float* W, int ldw, int M, int N, const float* bias, bool accumulate, float* C, int ldc,
+             cudaStream_t st) {
+  TcGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  int off = 0;
+  for (int s = 0; s < n_segs; ++s) {
+    g.seg[s].a = segs[s].a; g.seg[s].idx = segs[s].idx; g.seg[s].lda = segs[s].lda; g.seg[s].k = segs[s].k; g.seg[s].w_off = off;
+    off += segs[s].k;
+  }
+  g.n_segs = n_segs; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.bias = bias; g.accumulate = accumulate ? 1 : 0; g.C = C; g.ldc = ldc;
+  return launch_tc_gemm(g, 1, st);
+}
 int gemm(const float* A, const int* a_idx, int lda, const float* W, int ldw, int M, int N, int K, const float* bias, bool accumulate,
          float* C, int ldc, cudaStream_t st) {
-  if (M <= 0 || N <= 0) return 0;
-  dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, a_idx, lda, W, ldw, M, N, K, bias, accumulate ? 1 : 0, C, ldc);
-  return (int)cudaGetLastError();
+  const Seg sg = {A, a_idx, lda, K};
+  return gemm_cat(&sg, 1, W, ldw, M, N, bias, accumulate, C, ldc, st);
 }
 int row_act(float* X, int M, int Hd, const float* g, const float* b, int act, cudaStream_t st) {
   if (M <= 0) return 0;
@@ -324,10 +282,9 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
   // Linear -> LayerNorm -> ReLU -> Linear on the edge rows  kv = [r | h_dst | h_src | inv_dst]  (MLP of models/common.py:47-67)
   auto edge_mlp = [&](const std::string& p, const float* h, int n2, float* out) -> int {
     const float* w0 = P(p + ".net.0.weight");
-    SMB_G(gemm(grbf, nullptr, kRbf, w0, KV, M, H, kRbf, P(p + ".net.0.bias"), false, ghid, H, st));
-    SMB_G(gemm(h, dst_idx, H, w0 + kRbf, KV, M, H, H, nullptr, true, ghid, H, st));
-    SMB_G(gemm(h, src_idx, H, w0 + kRbf + H, KV, M, H, H, nullptr, true, ghid, H, st));
-    SMB_G(gemm(inv, mol_idx, kShape, w0 + kRbf + 2 * H, KV, M, H, kShape, nullptr, true, ghid, H, st));
+    // kv = [r | h_dst | h_src | inv_dst] (uni_transformer.py:61-63) as ONE gathered GEMM over the concatenated operand
+    const Seg kv[4] = {{grbf, nullptr, kRbf, kRbf}, {h, dst_idx, H, H}, {h, src_idx, H, H}, {inv, mol_idx, kShape, kShape}};
+    SMB_G(gemm_cat(kv, 4, w0, KV, M, H, P(p + ".net.0.bias"), false, ghid, H, st));
     SMB_G(row_act(ghid, M, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
     SMB_G(gemm(ghid, nullptr, H, P(p + ".net.3.weight"), H, M, n2, H, P(p + ".net.3.bias"), false, out, n2, st));
     return 0;
@@ -367,8 +324,8 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
     {
       const std::string p = x2h + ".node_output";
       const float* w0 = P(p + ".net.0.weight");
-      SMB_G(gemm(agg, nullptr, H, w0, 2 * H, N, H, H, P(p + ".net.0.bias"), false, gnode, H, st));
-      SMB_G(gemm(h_in, nullptr, H, w0 + H, 2 * H, N, H, H, nullptr, true, gnode, H, st));
+      const Seg cat[2] = {{agg, nullptr, H, H}, {h_in, nullptr, H, H}};     // [agg | h] (uni_transformer.py:82)
+      SMB_G(gemm_cat(cat, 2, w0, 2 * H, N, H, P(p + ".net.0.bias"), false, gnode, H, st));
       SMB_G(row_act(gnode, N, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
       SMB_CUDA_OK(cudaMemcpyAsync(h_out, h_in, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, st));   // residual (:87-88)
       SMB_G(gemm(gnode, nullptr, H, P(p + ".net.3.weight"), H, N, H, H, P(p + ".net.3.bias"), true, h_out, H, st));

@@ -140,6 +140,30 @@ int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* 
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 int debug_ws_trace(long long* host_out);   // -DSMB_DEBUG builds: [15 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
 
+// Gathered fp32 GEMM on tcgen05 with split-bf16 products (smb_tc_gemm.cu):
+//   C[M x N] (+)= [A_0[idx_0[m]] | ... | A_{n-1}[idx_{n-1}[m]]] . W[N][K]^T + bias,   K = sum of the segments' k
+struct TcGemmSeg {
+  const float* a;      // [rows][lda] fp32
+  const int* idx;      // row of `a` for output row m (NULL: m; negative: a zero row)
+  long long lda;
+  int k;               // columns of this segment
+  int w_off;           // first column of W this segment multiplies
+};
+struct TcGemmArgs {
+  TcGemmSeg seg[4];
+  int n_segs;
+  const float* W;      // [N][ldw] fp32
+  long long ldw;
+  int M, N;
+  const float* bias;   // [N] or NULL
+  int accumulate;      // C += ...
+  float* C;
+  long long ldc;
+  long long a_batch, w_batch, c_batch, idx_batch;   // element strides between the grid.z batches (0: shared)
+  int vec, vec_c;      // set by the launcher: 16-byte aligned operand / output rows
+};
+int launch_tc_gemm(const TcGemmArgs& g, int n_batch, cudaStream_t st);
+
 // generic-shape fp32 path (smb_generic.cu): hidden_dim != 128
 int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout& L, const Workspace& W, void* ws_base, const smb_batch& b,
                     const smb_forward_io& io, cudaStream_t st);

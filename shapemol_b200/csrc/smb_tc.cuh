@@ -80,26 +80,28 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
 }
-// A failed try_wait returns after a few cycles, so a bare retry loop re-issues twice per ~8 cycles and takes issue
-// slots from the working warps of its scheduler (measured: 35 % of all executed instructions): back off between tries.
+// A failed try_wait returns after a few cycles, so a bare retry loop re-issues twice per ~8 cycles and takes issue slots
+// from the working warps of its scheduler; with a fixed 20 ns back-off the polling (try_wait + nanosleep + branch) was still a
+// third of all executed instructions of the edge pipeline (ncu source page, round 2).  Exponential back-off: short waits stay
+// responsive, a warp that waits a whole pipeline stage polls a handful of times.  MAX_NS bounds the wake-up latency a waiter adds
+// to the hand-off (the single MMA-issuer warps use a small cap: their latency is on every tile's critical path).
+__device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+template <uint32_t MAX_NS = 256>
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-#ifdef SMB_MBAR_SUSPEND_HINT
-  // try_wait with an explicit suspend-time hint: the hardware parks the thread for up to that many nanoseconds
-  asm volatile("{\n\t.reg .pred P1;\n\t"
-               "WAIT_%=:\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-               "@!P1 bra WAIT_%=;\n\t"
-               "}\n" :: "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)SMB_MBAR_SUSPEND_HINT) : "memory");
-#else
-  asm volatile("{\n\t.reg .pred P1;\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-               "@P1 bra DONE_%=;\n\t"
-               "WAIT_%=:\n\t"
-               "nanosleep.u32 %2;\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-               "@!P1 bra WAIT_%=;\n\t"
-               "DONE_%=:\n\t}\n" :: "r"(smem_u32(b)), "r"(parity), "r"(20u) : "memory");
-#endif
+  if (mbar_try(b, parity)) return;
+  uint32_t ns = 32;
+#pragma unroll 1
+  while (true) {
+    asm volatile("nanosleep.u32 %0;" :: "r"(ns));
+    if (mbar_try(b, parity)) return;
+    ns = ns * 2 < MAX_NS ? ns * 2 : MAX_NS;
+  }
 }
 // busy-polling variant for the single MMA-issuer warps: their wake-up latency is on every tile's critical path
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* b, uint32_t parity) {
