@@ -11,10 +11,12 @@
 // three contiguous 128-float segments; the four block outputs are written side by side into one
 // [point][3][128*n_blocks] buffer, which is the concatenation conv_c consumes.
 //
-// Kernels (all fp32; the kNN selection of the dynamic graph needs fp32-faithful distances):
+// Kernels (fp32 data; the contractions run on tcgen05 with split-bf16 products, ~2^-16 per product, smb_tc_gemm.cu):
 //   enc_sqnorm_kernel      |f|^2 per point
-//   enc_knn_kernel         Gram tile (SIMT, smem-tiled) -> pd = -|fj|^2 + 2<fi,fj> - |fi|^2 -> top-k per row
-//   enc_gemm_kernel        node GEMM  [3*B*P x K] x [N x K]^T
+//   tc_gemm_kernel         Gram matrices F F^T of the hidden features, one cloud per grid.z (P <= 1024)
+//   enc_topk_kernel        pd = -|fj|^2 + 2<fi,fj> - |fi|^2 from the Gram row, held in registers -> top-k per row
+//   enc_knn_kernel         fp32 SIMT Gram tile + top-k: the coordinate graph of conv_pos (K = 3) and clouds of P > 1024
+//   tc_gemm_kernel         node GEMM  [3*B*P x K] x [N x K]^T
 //   enc_edge_stats_kernel  sum / sum of squares of |p_ij| per channel (BatchNorm2d batch statistics)
 //   enc_bn_final_kernel    fp64 reduction of the partials, running-stat update, scale | shift
 //   enc_edge_apply_kernel  VN batch-norm + directional leaky-ReLU + mean over k
@@ -35,10 +37,11 @@ constexpr float VN_EPS = 1e-6f;  // EPS of models/shape_vn_layers.py:6
 constexpr int STAT_CTAS = 148 * 8;
 
 struct Ws {
-  size_t xx, idx, h0, hc, uv, pc, w4, wc, part, bnp, total;
+  size_t xx, idx, h0, hc, uv, pc, w4, wc, part, bnp, gram, total;
 };
+constexpr int GRAM_MAX_P = 1024;   // clouds up to this size take the tensor-core Gram path (the top-k holds a row in registers)
 
-static Ws plan(int n_blocks, int latent, int k, size_t n_points) {
+static Ws plan(int n_blocks, int latent, int k, size_t n_points, int P) {
   (void)latent;
   Ws w;
   size_t o = 0;
@@ -53,6 +56,7 @@ static Ws plan(int n_blocks, int latent, int k, size_t n_points) {
   w.wc = take((size_t)PCW * HS * n_blocks * 4);
   w.part = take((size_t)STAT_CTAS * 2 * HS * 8);
   w.bnp = take(2 * HS * 4);
+  w.gram = take(P <= GRAM_MAX_P ? n_points * (size_t)P * 4 : 0);   // [B][P][P] fp32
   w.total = o;
   return w;
 }
@@ -167,57 +171,94 @@ __global__ void __launch_bounds__(256) enc_knn_kernel(const float* __restrict__ 
   }
 }
 
-// ---- node GEMM: C[M][ldc](N) = A[M][lda](K) * W[N][ldw](K)^T, fp32, 128x128 tile, BK = 16 ----------
-__global__ void __launch_bounds__(256) enc_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                       float* __restrict__ C, int ldc, size_t M, int N, int K) {
-  constexpr int STR = 132;
-  __shared__ __align__(16) float As[16 * STR];
-  __shared__ __align__(16) float Bs[16 * STR];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const size_t m0 = (size_t)blockIdx.x * 128;
-  const int n0 = blockIdx.y * 128;
-  float acc[8][8];
+// ---- node GEMM: C[M][ldc](N) = A[M][lda](K) * W[N][ldw](K)^T on tcgen05 (split-bf16 products, smb_tc_gemm.cu) ----------
+static int enc_gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, size_t M, int N, int K, cudaStream_t st) {
+  TcGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.seg[0].a = A; g.seg[0].lda = lda; g.seg[0].k = K;
+  g.n_segs = 1; g.W = W; g.ldw = ldw; g.M = (int)M; g.N = N; g.C = C; g.ldc = ldc;
+  g.split3 = 1;   // fp32-level products: the next layer's kNN graph is selected on these features
+  return launch_tc_gemm(g, 1, st);
+}
+
+// ---- kNN from a Gram matrix (P <= GRAM_MAX_P): G = F F^T per cloud on tcgen05, then one warp per row keeps the row's
+// pd[j] = (-|f_j|^2 + 2 G_ij) - |f_i|^2 in registers and extracts the K2 = k + 8 largest (ties: smaller index first).
+// The three-piece Gram entries are fp32-level (operand split ~2^-23, fp32 accumulation over K = 384); whenever the k-th and
+// (k+1)-th candidates are closer than 3e-5 of |f_i|^2 (exact ties included) the K2 candidates are re-evaluated with an fp64-accumulated dot product of the fp32
+// features and the k nearest are selected from those values. ----
+template <int NV>
+__global__ void __launch_bounds__(256) enc_topk_kernel(const float* __restrict__ gram, const float* __restrict__ xx,
+                                                       const float* __restrict__ feat, size_t row_stride, int segs, int seg_len,
+                                                       int seg_stride, int P, int k, size_t n_points, int* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_points) return;
+  const size_t base = row / P * P;
+  const float* g = gram + row * P;
+  const float xr = xx[row];
+  float v[NV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int q = 0; q < NV; ++q) {
+    const int c = q * 32 + lane;
+    v[q] = c < P ? (-xx[base + c] - (-2.f * g[c])) - xr : -INFINITY;     // same association as the reference expression
+  }
+  const int K2 = min(min(k + 8, 32), P);
+  int my_idx = 0x7fffffff;
+  float my_pd = -INFINITY;
+  for (int s = 0; s < K2; ++s) {
+    float best = -INFINITY;
+    int bq = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    __syncthreads();
+    for (int q = 0; q < NV; ++q)
+      if (v[q] > best) { best = v[q]; bq = q; }      // ascending scan keeps the smallest index among equals
+    int bi = best > -INFINITY ? bq * 32 + lane : 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = (tid >> 2) + 64 * i, k4 = (tid & 3) * 4;
-      float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
-      if (m0 + r < M) av = *reinterpret_cast<const float4*>(A + (m0 + r) * lda + k0 + k4);
-      if (n0 + r < N) bv = *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * ldw + k0 + k4);
-      As[(k4 + 0) * STR + r] = av.x; As[(k4 + 1) * STR + r] = av.y; As[(k4 + 2) * STR + r] = av.z; As[(k4 + 3) * STR + r] = av.w;
-      Bs[(k4 + 0) * STR + r] = bv.x; Bs[(k4 + 1) * STR + r] = bv.y; Bs[(k4 + 2) * STR + r] = bv.z; Bs[(k4 + 3) * STR + r] = bv.w;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    __syncthreads();
+    if (bi >= P) bi = (int)(row - base);          // fewer than K2 finite candidates (never for K2 <= P)
+    if (lane == s) { my_idx = bi; my_pd = best; }
+    if ((bi & 31) == lane) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const float4 a0 = *reinterpret_cast<const float4*>(As + q * STR + ty * 8), a1 = *reinterpret_cast<const float4*>(As + q * STR + ty * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(Bs + q * STR + tx * 8), b1 = *reinterpret_cast<const float4*>(Bs + q * STR + tx * 8 + 4);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      for (int q = 0; q < NV; ++q)
+        if (q == (bi >> 5)) v[q] = -INFINITY;
     }
   }
+  // unambiguous boundary: the approximate order of the first k is the answer
+  const float tk = __shfl_sync(0xffffffffu, my_pd, k - 1), tk1 = K2 > k ? __shfl_sync(0xffffffffu, my_pd, k) : -INFINITY;
+  const float tol = 3e-5f * (fabsf(tk) + fabsf(xr) + 1e-30f);
+  if (!(tk - tk1 <= tol)) {
+    if (lane < k) idx[row * k + lane] = my_idx;
+    return;
+  }
+  // exact re-evaluation of the K2 candidates
+  const float* fi = feat + row * row_stride;
+  for (int c = 0; c < K2; ++c) {
+    const int j = __shfl_sync(0xffffffffu, my_idx, c);
+    const float* fj = feat + (base + j) * row_stride;
+    double acc = 0.0;
+    for (int sg = 0; sg < segs; ++sg)
+      for (int e = lane; e < seg_len; e += 32)
+        acc = fma((double)fi[(size_t)sg * seg_stride + e], (double)fj[(size_t)sg * seg_stride + e], acc);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const size_t m = m0 + ty * 8 + i;
-    if (m >= M) continue;
-    float* crow = C + m * ldc + n0 + tx * 8;
-    if (n0 + tx * 8 + 8 <= N) {
-      *reinterpret_cast<float4*>(crow) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      *reinterpret_cast<float4*>(crow + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-    } else {
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float ex = (-xx[base + j] - (-2.f * (float)acc)) - xr;
+    if (lane == c) my_pd = ex;
+  }
+  if (lane >= K2) { my_pd = -INFINITY; my_idx = 0x7fffffff; }
+  for (int s = 0; s < k; ++s) {
+    float best = my_pd;
+    int bi = my_idx;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (n0 + tx * 8 + j < N) crow[j] = acc[i][j];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
+    if (lane == 0) idx[row * k + s] = bi;
+    if (my_idx == bi) my_pd = -INFINITY;
   }
 }
 
@@ -427,11 +468,30 @@ static int launch_knn_t(const float* feat, size_t row_stride, int segs, int seg_
 }
 
 static int launch_knn(const float* feat, size_t row_stride, int segs, int seg_len, int seg_stride, float* xx, int B, int P, int k,
-                      int* idx, cudaStream_t st) {
+                      int* idx, float* gram, cudaStream_t st) {
   const size_t n_points = (size_t)B * P;
   enc_sqnorm_kernel<<<(unsigned)((n_points + 7) / 8), 256, 0, st>>>(feat, row_stride, segs, seg_len, seg_stride, n_points, xx);
   int rc = (int)cudaGetLastError();
   if (rc) return rc;
+  if (gram && P <= GRAM_MAX_P && seg_len >= 32 && segs <= 4 && k <= 24) {
+    // hidden features (R^384): Gram matrices on the tensor pipe, the three coordinate segments as concatenated operands
+    TcGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    for (int sg = 0; sg < segs; ++sg) {
+      g.seg[sg].a = feat + (size_t)sg * seg_stride; g.seg[sg].lda = (long long)row_stride; g.seg[sg].k = seg_len;
+      g.seg[sg].w_off = sg * seg_stride;
+    }
+    g.n_segs = segs; g.W = feat; g.ldw = (long long)row_stride; g.M = P; g.N = P; g.C = gram; g.ldc = P;
+    g.a_batch = g.w_batch = (long long)P * (long long)row_stride; g.c_batch = (long long)P * P;
+    g.split3 = 1;
+    rc = launch_tc_gemm(g, B, st);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((n_points + 7) / 8);
+    if (P <= 256) enc_topk_kernel<8><<<grid, 256, 0, st>>>(gram, xx, feat, row_stride, segs, seg_len, seg_stride, P, k, n_points, idx);
+    else if (P <= 512) enc_topk_kernel<16><<<grid, 256, 0, st>>>(gram, xx, feat, row_stride, segs, seg_len, seg_stride, P, k, n_points, idx);
+    else enc_topk_kernel<32><<<grid, 256, 0, st>>>(gram, xx, feat, row_stride, segs, seg_len, seg_stride, P, k, n_points, idx);
+    return (int)cudaGetLastError();
+  }
   switch (knn_rows(P)) {
     case 32: return launch_knn_t<4>(feat, row_stride, segs, seg_len, seg_stride, xx, B, P, k, idx, st);
     case 16: return launch_knn_t<2>(feat, row_stride, segs, seg_len, seg_stride, xx, B, P, k, idx, st);
@@ -455,7 +515,7 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
                   cudaStream_t st) {
   const size_t n_points = (size_t)B * P, n_rows = n_points * 3;
   const int k = w.num_k, nb = w.n_blocks, HC = HS * nb;
-  const Ws L = plan(nb, w.latent, k, n_points);
+  const Ws L = plan(nb, w.latent, k, n_points, P);
   if (!ws_base || ws_bytes < L.total) { set_error_msg("smb_vn_dgcnn_encode: workspace too small"); return SMB_E_BADARG; }
   unsigned char* base = reinterpret_cast<unsigned char*>(ws_base);
   float* xx = reinterpret_cast<float*>(base + L.xx);
@@ -468,11 +528,12 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
   float* wc = reinterpret_cast<float*>(base + L.wc);
   double* part = reinterpret_cast<double*>(base + L.part);
   float* bnp = reinterpret_cast<float*>(base + L.bnp);
+  float* gram = P <= GRAM_MAX_P ? reinterpret_cast<float*>(base + L.gram) : nullptr;
   const int stat_grid = (int)(n_points < (size_t)STAT_CTAS ? n_points : (size_t)STAT_CTAS);
   const double edge_count = (double)n_points * (double)k;
 
   // ---- conv_pos on the kNN graph of the coordinates (shape_pointcloud_modelAE.py:241-243) ----
-  ENC_LAUNCH(launch_knn(clouds, 3, 1, 3, 0, xx, B, P, k, idx, st));
+  ENC_LAUNCH(launch_knn(clouds, 3, 1, 3, 0, xx, B, P, k, idx, nullptr, st));
   ENC_KERNEL(enc_prep_w4_kernel<<<1, HS, 0, st>>>(w.conv_pos_feat, w.conv_pos_dir, 1, w4));
   ENC_KERNEL(enc_pos_uv_kernel<<<(unsigned)((n_rows * (UVW / 4) + 255) / 256), 256, 0, st>>>(clouds, w4, n_rows, uv));
   ENC_KERNEL(enc_edge_stats_kernel<<<stat_grid, HS, 0, st>>>(uv, idx, P, k, n_points, part));
@@ -484,9 +545,9 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
   for (int i = 0; i < nb; ++i) {
     const float* in = i == 0 ? h0 : hc + (size_t)(i - 1) * HS;
     const int ldi = i == 0 ? HS : HC;
-    ENC_LAUNCH(launch_knn(in, (size_t)3 * ldi, 3, HS, ldi, xx, B, P, k, idx, st));
+    ENC_LAUNCH(launch_knn(in, (size_t)3 * ldi, 3, HS, ldi, xx, B, P, k, idx, gram, st));
     ENC_KERNEL(enc_prep_w4_kernel<<<(HS * HS + 255) / 256, 256, 0, st>>>(w.block_feat[i], w.block_dir[i], HS, w4));
-    ENC_KERNEL(enc_gemm_kernel<<<dim3((unsigned)((n_rows + 127) / 128), UVW / 128), 256, 0, st>>>(in, ldi, w4, HS, uv, UVW, n_rows, UVW, HS));
+    ENC_LAUNCH(enc_gemm(in, ldi, w4, HS, uv, UVW, n_rows, UVW, HS, st));
     ENC_KERNEL(enc_edge_stats_kernel<<<stat_grid, HS, 0, st>>>(uv, idx, P, k, n_points, part));
     ENC_KERNEL(enc_bn_final_kernel<<<1, HS, 0, st>>>(part, stat_grid, HS, edge_count, 1, w.block_bn_w[i], w.block_bn_b[i],
                                                      w.block_bn_rm[i], w.block_bn_rv[i], bnp));
@@ -497,7 +558,7 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
   SMB_CUDA_OK(cudaMemsetAsync(wc, 0, (size_t)PCW * HC * 4, st));
   SMB_CUDA_OK(cudaMemcpyAsync(wc, w.conv_c_feat, (size_t)w.latent * HC * 4, cudaMemcpyDeviceToDevice, st));
   SMB_CUDA_OK(cudaMemcpyAsync(wc + (size_t)w.latent * HC, w.conv_c_dir, (size_t)HC * 4, cudaMemcpyDeviceToDevice, st));
-  ENC_KERNEL(enc_gemm_kernel<<<dim3((unsigned)((n_rows + 127) / 128), 1), 256, 0, st>>>(hc, HC, wc, HC, pc, PCW, n_rows, w.latent + 1, HC));
+  ENC_LAUNCH(enc_gemm(hc, HC, wc, HC, pc, PCW, n_rows, w.latent + 1, HC, st));
   const int c_grid = (int)((n_points + 7) / 8 < (size_t)STAT_CTAS ? (n_points + 7) / 8 : (size_t)STAT_CTAS);
   ENC_KERNEL(enc_c_stats_kernel<<<c_grid, 256, 0, st>>>(pc, w.latent, n_points, part));
   ENC_KERNEL(enc_bn_final_kernel<<<1, HS, 0, st>>>(part, c_grid, w.latent, (double)n_points, w.training, w.conv_c_bn_w, w.conv_c_bn_b,
@@ -514,7 +575,7 @@ extern "C" {
 size_t smb_encoder_workspace_bytes(const smb_encoder_weights* w, int32_t n_clouds, int32_t n_points) {
   if (smb::enc::check(w, n_clouds, n_points)) return 0;
   const size_t n = (size_t)(n_clouds > 0 ? n_clouds : 1) * (size_t)(n_points > 0 ? n_points : 1);
-  return smb::enc::plan(w->n_blocks, w->latent, w->num_k, n).total;
+  return smb::enc::plan(w->n_blocks, w->latent, w->num_k, n, n_points > 0 ? n_points : 1).total;
 }
 
 int smb_vn_dgcnn_encode(const smb_encoder_weights* w, const float* clouds, int32_t n_clouds, int32_t n_points, float* latent,

@@ -160,6 +160,7 @@ struct TcGemmArgs {
   float* C;
   long long ldc;
   long long a_batch, w_batch, c_batch, idx_batch;   // element strides between the grid.z batches (0: shared)
+  int split3;          // three bf16 pieces per operand (fp32-level products, six MMAs per step) instead of two
   int vec, vec_c;      // set by the launcher: 16-byte aligned operand / output rows
 };
 int launch_tc_gemm(const TcGemmArgs& g, int n_batch, cudaStream_t st);

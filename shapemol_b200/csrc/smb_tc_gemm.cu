@@ -7,9 +7,11 @@
 // of the generic path and its [E, hidden] intermediate is written once.  Also used (batched, one cloud per grid.z) for the
 // VN-DGCNN encoder's node GEMMs and Gram matrices (models/shape_vn_layers.py:257-292).
 //
-// Every operand element is split x = hi + lo (two bf16, 16 significant bits) while it is staged to shared memory, and a K = 16
-// step is three MMAs  hi.hi + lo.hi + hi.lo : products agree with fp32 to ~2^-16, which keeps the 1e-3 parity bar (and the
-// fp32 ranking of the encoder's kNN) with a wide margin.  The kernel is tensor-pipe bound by construction (3 x 128 x N x 16 per
+// Every operand element is split into bf16 pieces while it is staged to shared memory.  Two pieces x = hi + lo (16 significant
+// bits), three MMAs per K = 16 step (hi.hi + lo.hi + hi.lo): products agree with fp32 to ~2^-16, which keeps the 1e-3 parity
+// bar of the denoiser with a wide margin.  Three pieces (TcGemmArgs::split3; 24 significant bits, six MMAs): fp32-level
+// products, for the encoder, whose dynamic kNN graphs are selected on these values -- a 1e-5 perturbation of the features
+// flips near-tie neighbours against the reference's fp32 graph.  The kernel is tensor-pipe bound by construction (3 x 128 x N x 16 per
 // step against ~2.5 staged elements per thread and step).
 //
 // CTA = 128 rows x N_TILE <= 256 columns, 256 threads, K consumed in chunks of 32 through a two-stage shared-memory ring; all
@@ -25,14 +27,53 @@ namespace {
 
 using namespace tc;
 
-constexpr int TM = 128, KC = 32, NT_MAX = 256, THREADS = 256;
-constexpr int A_BYTES = TM * KC * 2;          // 8 KB  (one of hi / lo)
-constexpr int W_BYTES = NT_MAX * KC * 2;      // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // 48 KB
-constexpr int SBO = (KC / 8) * 128;           // 512
-constexpr int SMEM_TOTAL = 128 + 2 * STAGE_BYTES;
+constexpr int TM = 128, NT_MAX = 256, THREADS = 256;
 
+// SPLIT = 2: x = hi + lo            (16 significant bits), products hh + lh + hl                    (~2^-16 per product)
+// SPLIT = 3: x = hi + mid + lo      (24 significant bits), products hh + hm + mh + mm + hl + lh     (~2^-23: fp32 level)
+template <int SPLIT>
+struct Cfg {
+  static constexpr int KC = SPLIT == 3 ? 16 : 32;          // k per stage: keeps two CTAs (<= 96 KB each) per SM
+  static constexpr int A_BYTES = TM * KC * 2;              // one piece
+  static constexpr int W_BYTES = NT_MAX * KC * 2;
+  static constexpr int STAGE_BYTES = SPLIT * (A_BYTES + W_BYTES);
+  static constexpr int SBO = (KC / 8) * 128;
+  static constexpr int SMEM_TOTAL = 128 + 2 * STAGE_BYTES;
+  static constexpr int N_TERMS = SPLIT == 3 ? 6 : 3;
+};
+__device__ __constant__ int kTermA[6] = {0, 1, 0, 1, 0, 2}, kTermW[6] = {0, 0, 1, 1, 2, 0};
+
+// eight consecutive values -> one 16-byte K-major chunk per piece
+template <int SPLIT>
+__device__ __forceinline__ void split_store(const float (&v)[8], unsigned char* dst, int piece_stride) {
+  uint32_t p[SPLIT][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a = v[2 * q], b = v[2 * q + 1];
+#pragma unroll
+    for (int s = 0; s < SPLIT; ++s) {
+      p[s][q] = pack_bf16(a, b);
+      if (s + 1 < SPLIT) { a -= __uint_as_float(p[s][q] << 16); b -= __uint_as_float(p[s][q] & 0xffff0000u); }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < SPLIT; ++s) *reinterpret_cast<uint4*>(dst + s * piece_stride) = make_uint4(p[s][0], p[s][1], p[s][2], p[s][3]);
+}
+
+__device__ __forceinline__ float4 load4(const float* p, int k, int kmax, bool vec) {
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec && k + 3 < kmax) return __ldg(reinterpret_cast<const float4*>(p + k));
+  if (k < kmax) x.x = __ldg(p + k);
+  if (k + 1 < kmax) x.y = __ldg(p + k + 1);
+  if (k + 2 < kmax) x.z = __ldg(p + k + 2);
+  if (k + 3 < kmax) x.w = __ldg(p + k + 3);
+  return x;
+}
+
+template <int SPLIT>
 __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
+  using C = Cfg<SPLIT>;
+  constexpr int KC = C::KC, A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES, SBO = C::SBO;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);            // [0], [1]: stage free; [2]: all MMAs done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
@@ -54,94 +95,68 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = idesc_bf16(n_tile, false);
 
-  // this thread's A row (two threads per row, 16 of the chunk's 32 k each)
-  const int ar = tid >> 1, ah = tid & 1;
+  // this thread's share of an A stage: 16 consecutive k of one row (KC / 16 threads per row)
+  constexpr int TPR = KC / 16;
+  const int ar = tid / TPR, ah = tid % TPR;
+  const bool a_thread = ar < TM;
   const int am = m0 + ar;
 
   int c = 0;
   for (int s = 0; s < g.n_segs; ++s) {
     const TcGemmSeg sg = g.seg[s];
     long long arow = -1;
-    if (am < g.M) arow = sg.idx ? (long long)sg.idx[bz * g.idx_batch + am] : (long long)am;
+    if (a_thread && am < g.M) arow = sg.idx ? (long long)sg.idx[bz * g.idx_batch + am] : (long long)am;
     const float* ap = arow >= 0 ? sg.a + bz * g.a_batch + arow * sg.lda : nullptr;
     const float* wp = g.W + bz * g.w_batch + sg.w_off;
     for (int k0 = 0; k0 < sg.k; k0 += KC, ++c) {
       const int st = c & 1;
-      unsigned char* sa_hi = stages + st * STAGE_BYTES;
-      unsigned char* sa_lo = sa_hi + A_BYTES;
-      unsigned char* sw_hi = sa_lo + A_BYTES;
-      unsigned char* sw_lo = sw_hi + W_BYTES;
+      unsigned char* sa = stages + st * STAGE_BYTES;     // A pieces, then W pieces
+      unsigned char* sw = sa + SPLIT * A_BYTES;
       if (c >= 2) mbar_wait(bar + st, ((c >> 1) - 1) & 1);   // the MMAs of chunk c - 2 have read this stage
-      // ---- A: 16 consecutive k of one row -> two 16-byte K-major chunks, hi and lo ----
-      {
-        float v[16];
+      // ---- A: 16 consecutive k of one row -> two 16-byte K-major chunks per piece ----
+      if (a_thread) {
         const int kb = k0 + ah * 16;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int k = kb + 4 * q;
-          if (ap) {
-            if (g.vec && k + 3 < sg.k) x = __ldg(reinterpret_cast<const float4*>(ap + k));
-            else {
-              if (k < sg.k) x.x = __ldg(ap + k);
-              if (k + 1 < sg.k) x.y = __ldg(ap + k + 1);
-              if (k + 2 < sg.k) x.z = __ldg(ap + k + 2);
-              if (k + 3 < sg.k) x.w = __ldg(ap + k + 3);
-            }
-          }
-          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        }
         const int off = (ar >> 3) * SBO + (ar & 7) * 16 + ah * 256;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) split_bf16<false>(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], hi[q], lo[q]);
-          *reinterpret_cast<uint4*>(sa_hi + off + j * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sa_lo + off + j * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
-      // ---- W: row n of the weight, the chunk's 32 k -> four K-major chunks, hi and lo ----
-      for (int n = tid; n < n_tile; n += THREADS) {
-        const bool nv = n0 + n < g.N;
-        const float* wr = wp + (long long)(n0 + n) * g.ldw + k0;
-        const int off = (n >> 3) * SBO + (n & 7) * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
           float v[8];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int k = 8 * j + 4 * q;
-            if (nv) {
-              if (g.vec && k0 + k + 3 < sg.k) x = __ldg(reinterpret_cast<const float4*>(wr + k));
-              else {
-                if (k0 + k < sg.k) x.x = __ldg(wr + k);
-                if (k0 + k + 1 < sg.k) x.y = __ldg(wr + k + 1);
-                if (k0 + k + 2 < sg.k) x.z = __ldg(wr + k + 2);
-                if (k0 + k + 3 < sg.k) x.w = __ldg(wr + k + 3);
-              }
-            }
+            const float4 x = ap ? load4(ap, kb + 8 * j + 4 * q, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
             v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
           }
-          uint32_t hi[4], lo[4];
+          split_store<SPLIT>(v, sa + off + j * 128, A_BYTES);
+        }
+      }
+      // ---- W: row n of the weight, the chunk's KC k -> KC / 8 K-major chunks per piece ----
+      for (int n = tid; n < n_tile; n += THREADS) {
+        const bool nv = n0 + n < g.N;
+        const float* wr = wp + (long long)(n0 + n) * g.ldw;
+        const int off = (n >> 3) * SBO + (n & 7) * 16;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_bf16<false>(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-          *reinterpret_cast<uint4*>(sw_hi + off + j * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sw_lo + off + j * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int j = 0; j < KC / 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 x = nv ? load4(wr, k0 + 8 * j + 4 * q, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+          }
+          split_store<SPLIT>(v, sw + off + j * 128, W_BYTES);
         }
       }
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
-        const uint32_t a_hi = smem_u32(sa_hi), a_lo = smem_u32(sa_lo), w_hi = smem_u32(sw_hi), w_lo = smem_u32(sw_lo);
+        const uint32_t a0 = smem_u32(sa), w0 = smem_u32(sw);
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {
-          mma_ss(tmem, smem_desc(a_hi + ks * 256, 128, SBO), smem_desc(w_hi + ks * 256, 128, SBO), idesc, (c | ks) > 0);
-          mma_ss(tmem, smem_desc(a_lo + ks * 256, 128, SBO), smem_desc(w_hi + ks * 256, 128, SBO), idesc, 1);
-          mma_ss(tmem, smem_desc(a_hi + ks * 256, 128, SBO), smem_desc(w_lo + ks * 256, 128, SBO), idesc, 1);
-        }
+        for (int ks = 0; ks < KC / 16; ++ks)
+#pragma unroll
+          for (int t = 0; t < C::N_TERMS; ++t) {
+            const int pa = SPLIT == 3 ? kTermA[t] : (t == 1 ? 1 : 0), pw = SPLIT == 3 ? kTermW[t] : (t == 2 ? 1 : 0);
+            mma_ss(tmem, smem_desc(a0 + pa * A_BYTES + ks * 256, 128, SBO), smem_desc(w0 + pw * W_BYTES + ks * 256, 128, SBO), idesc,
+                   (c | ks | t) > 0);
+          }
         mma_commit(bar + st);
       }
     }
@@ -201,10 +216,16 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
     vec = vec && aligned16(g.seg[s].a) && g.seg[s].lda % 4 == 0 && g.seg[s].w_off % 4 == 0 && g.a_batch % 4 == 0;
   g.vec = vec ? 1 : 0;
   g.vec_c = (aligned16(g.C) && g.ldc % 4 == 0 && g.c_batch % 4 == 0) ? 1 : 0;
-  static size_t configured[kMaxDevices] = {};
-  if (int rc = ensure_dynamic_smem(tc_gemm_kernel, SMEM_TOTAL, configured)) return rc;
   const dim3 grid((unsigned)((g.M + TM - 1) / TM), (unsigned)((g.N + NT_MAX - 1) / NT_MAX), (unsigned)n_batch);
-  tc_gemm_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(g);
+  if (g.split3) {
+    static size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_dynamic_smem(tc_gemm_kernel<3>, Cfg<3>::SMEM_TOTAL, configured)) return rc;
+    tc_gemm_kernel<3><<<grid, THREADS, Cfg<3>::SMEM_TOTAL, st>>>(g);
+  } else {
+    static size_t configured[kMaxDevices] = {};
+    if (int rc = ensure_dynamic_smem(tc_gemm_kernel<2>, Cfg<2>::SMEM_TOTAL, configured)) return rc;
+    tc_gemm_kernel<2><<<grid, THREADS, Cfg<2>::SMEM_TOTAL, st>>>(g);
+  }
   return (int)cudaGetLastError();
 }
 
