@@ -14,9 +14,10 @@
 // flips near-tie neighbours against the reference's fp32 graph.  The kernel is tensor-pipe bound by construction (3 x 128 x N x 16 per
 // step against ~2.5 staged elements per thread and step).
 //
-// CTA = 128 rows x N_TILE <= 256 columns, 256 threads, K consumed in chunks of 32 through a two-stage shared-memory ring; all
-// threads stage (gather, split, K-major store), thread 0 issues the MMAs and commits the stage's mbarrier; two CTAs per SM
-// (96 KB of shared memory, 256 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
+// CTA = 128 rows x N_TILE <= 256 columns, K consumed in chunks of 32 (16 with three pieces) through a two-stage shared-memory
+// ring: eight warps stage (gather with a one-chunk register prefetch, split, K-major store) and arrive on the stage's "full"
+// mbarrier, a ninth warp issues the MMAs and commits the stage's "free" mbarrier; two CTAs per SM (<= 96 KB of shared memory,
+// 256 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
 #include "smb_common.cuh"
 #include "smb_kernels.h"
 #include "smb_tc.cuh"
@@ -27,7 +28,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int TM = 128, NT_MAX = 256, THREADS = 256;
+constexpr int TM = 128, NT_MAX = 256, STAGERS = 256, THREADS = STAGERS + 32;   // 8 staging / epilogue warps + the MMA issuer
 
 // SPLIT = 2: x = hi + lo            (16 significant bits), products hh + lh + hl                    (~2^-16 per product)
 // SPLIT = 3: x = hi + mid + lo      (24 significant bits), products hh + hm + mh + mm + hl + lh     (~2^-23: fp32 level)
@@ -41,7 +42,6 @@ struct Cfg {
   static constexpr int SMEM_TOTAL = 128 + 2 * STAGE_BYTES;
   static constexpr int N_TERMS = SPLIT == 3 ? 6 : 3;
 };
-__device__ __constant__ int kTermA[6] = {0, 1, 0, 1, 0, 2}, kTermW[6] = {0, 0, 1, 1, 2, 0};
 
 // eight consecutive values -> one 16-byte K-major chunk per piece
 template <int SPLIT>
@@ -60,6 +60,21 @@ __device__ __forceinline__ void split_store(const float (&v)[8], unsigned char* 
   for (int s = 0; s < SPLIT; ++s) *reinterpret_cast<uint4*>(dst + s * piece_stride) = make_uint4(p[s][0], p[s][1], p[s][2], p[s][3]);
 }
 
+// four consecutive values -> 8 bytes (half a K-major chunk) per piece
+template <int SPLIT>
+__device__ __forceinline__ void split_store4(const float4& x, unsigned char* dst, int piece_stride) {
+  float a = x.x, b = x.y, c = x.z, d = x.w;
+#pragma unroll
+  for (int s = 0; s < SPLIT; ++s) {
+    const uint32_t p0 = pack_bf16(a, b), p1 = pack_bf16(c, d);
+    *reinterpret_cast<uint2*>(dst + s * piece_stride) = make_uint2(p0, p1);
+    if (s + 1 < SPLIT) {
+      a -= __uint_as_float(p0 << 16); b -= __uint_as_float(p0 & 0xffff0000u);
+      c -= __uint_as_float(p1 << 16); d -= __uint_as_float(p1 & 0xffff0000u);
+    }
+  }
+}
+
 __device__ __forceinline__ float4 load4(const float* p, int k, int kmax, bool vec) {
   float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
   if (vec && k + 3 < kmax) return __ldg(reinterpret_cast<const float4*>(p + k));
@@ -75,7 +90,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   using C = Cfg<SPLIT>;
   constexpr int KC = C::KC, A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES, SBO = C::SBO;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);            // [0], [1]: stage free; [2]: all MMAs done
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);            // [0], [1]: stage free; [2]: all MMAs done; [3], [4]: stage full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
   unsigned char* stages = smem + 128;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,6 +102,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid == 32) {
     mbar_init(bar + 0, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
+    mbar_init(bar + 3, STAGERS); mbar_init(bar + 4, STAGERS);
     mbar_init_fence();
   }
   fence_before_sync();
@@ -95,78 +111,89 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = idesc_bf16(n_tile, false);
 
-  // this thread's share of an A stage: 16 consecutive k of one row (KC / 16 threads per row)
-  constexpr int TPR = KC / 16;
-  const int ar = tid / TPR, ah = tid % TPR;
-  const bool a_thread = ar < TM;
-  const int am = m0 + ar;
+  // Staging map (coalesced): a chunk row is KC / 4 pieces of 16 bytes; consecutive lanes take consecutive pieces of a row, so a
+  // warp's load touches 4 (8) whole rows = 4 (8) cache lines instead of one line per lane.  Thread t: piece t % PPR of the rows
+  // t / PPR + (256 / PPR) i.  The global loads of chunk c + 1 are issued (into registers) right after chunk c has been stored
+  // to shared memory, so their latency overlaps the MMA issue and the wait for the stage to drain.
+  constexpr int PPR = KC / 4;                        // pieces per row
+  constexpr int RSTEP = STAGERS / PPR;               // rows covered by one pass of the 256 staging threads
+  constexpr int NA = TM / RSTEP, NW = NT_MAX / RSTEP;   // pieces per thread and chunk
+  const int sp = tid % PPR, sr = tid / PPR;
+  int n_chunks = 0;
+  for (int s = 0; s < g.n_segs; ++s) n_chunks += (g.seg[s].k + KC - 1) / KC;
 
-  int c = 0;
-  for (int s = 0; s < g.n_segs; ++s) {
-    const TcGemmSeg sg = g.seg[s];
-    long long arow = -1;
-    if (a_thread && am < g.M) arow = sg.idx ? (long long)sg.idx[bz * g.idx_batch + am] : (long long)am;
-    const float* ap = arow >= 0 ? sg.a + bz * g.a_batch + arow * sg.lda : nullptr;
-    const float* wp = g.W + bz * g.w_batch + sg.w_off;
-    for (int k0 = 0; k0 < sg.k; k0 += KC, ++c) {
+  if (warp == STAGERS / 32) {
+    // =========== MMA issuer: its own warp, so that issuing (~60 cycles per MMA, ~150 per commit) never delays the staging ===========
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
       const int st = c & 1;
-      unsigned char* sa = stages + st * STAGE_BYTES;     // A pieces, then W pieces
-      unsigned char* sw = sa + SPLIT * A_BYTES;
-      if (c >= 2) mbar_wait(bar + st, ((c >> 1) - 1) & 1);   // the MMAs of chunk c - 2 have read this stage
-      // ---- A: 16 consecutive k of one row -> two 16-byte K-major chunks per piece ----
-      if (a_thread) {
-        const int kb = k0 + ah * 16;
-        const int off = (ar >> 3) * SBO + (ar & 7) * 16 + ah * 256;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 x = ap ? load4(ap, kb + 8 * j + 4 * q, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-          }
-          split_store<SPLIT>(v, sa + off + j * 128, A_BYTES);
-        }
-      }
-      // ---- W: row n of the weight, the chunk's KC k -> KC / 8 K-major chunks per piece ----
-      for (int n = tid; n < n_tile; n += THREADS) {
-        const bool nv = n0 + n < g.N;
-        const float* wr = wp + (long long)(n0 + n) * g.ldw;
-        const int off = (n >> 3) * SBO + (n & 7) * 16;
-#pragma unroll
-        for (int j = 0; j < KC / 8; ++j) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 x = nv ? load4(wr, k0 + 8 * j + 4 * q, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-          }
-          split_store<SPLIT>(v, sw + off + j * 128, W_BYTES);
-        }
-      }
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        fence_after_sync();
-        const uint32_t a0 = smem_u32(sa), w0 = smem_u32(sw);
+      mbar_wait<32>(bar + 3 + st, (c >> 1) & 1);
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t a0 = smem_u32(stages + st * STAGE_BYTES), w0 = a0 + SPLIT * A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < KC / 16; ++ks)
 #pragma unroll
           for (int t = 0; t < C::N_TERMS; ++t) {
-            const int pa = SPLIT == 3 ? kTermA[t] : (t == 1 ? 1 : 0), pw = SPLIT == 3 ? kTermW[t] : (t == 2 ? 1 : 0);
+            const int pa = SPLIT == 3 ? (t == 1 || t == 3 ? 1 : t == 5 ? 2 : 0) : (t == 1 ? 1 : 0);
+            const int pw = SPLIT == 3 ? (t == 2 || t == 3 ? 1 : t == 4 ? 2 : 0) : (t == 2 ? 1 : 0);
             mma_ss(tmem, smem_desc(a0 + pa * A_BYTES + ks * 256, 128, SBO), smem_desc(w0 + pw * W_BYTES + ks * 256, 128, SBO), idesc,
                    (c | ks | t) > 0);
           }
         mma_commit(bar + st);
+        if (c + 1 == n_chunks) mma_commit(bar + 2);
       }
+      __syncwarp();
     }
+  } else {
+
+  float4 ra[NA], rw[NW];                // this thread's pieces of the staged chunk (fp32)
+  auto fetch = [&](int c) {             // chunk c -> (segment, k0)
+    int s = 0, k0 = c * KC;
+    while (k0 >= g.seg[s].k) { k0 -= (g.seg[s].k + KC - 1) / KC * KC; ++s; }
+    const TcGemmSeg& sg = g.seg[s];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int m = m0 + sr + RSTEP * i;
+      long long arow = -1;
+      if (m < g.M) arow = sg.idx ? (long long)__ldg(sg.idx + bz * g.idx_batch + m) : (long long)m;
+      ra[i] = arow >= 0 ? load4(sg.a + bz * g.a_batch + arow * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wb = g.W + bz * g.w_batch + sg.w_off;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const int n = sr + RSTEP * i;
+      rw[i] = (n < n_tile && n0 + n < g.N) ? load4(wb + (long long)(n0 + n) * g.ldw, k0 + 4 * sp, sg.k, g.vec != 0)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (n_chunks > 0) fetch(0);
+  const int poff = (sp >> 1) * 128 + (sp & 1) * 8;    // piece position inside a K-major row
+  for (int c = 0; c < n_chunks; ++c) {
+    const int st = c & 1;
+    unsigned char* sa = stages + st * STAGE_BYTES;     // A pieces, then W pieces
+    unsigned char* sw = sa + SPLIT * A_BYTES;
+    if (c >= 2) mbar_wait(bar + st, ((c >> 1) - 1) & 1);   // the MMAs of chunk c - 2 have read this stage
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int r = sr + RSTEP * i;
+      split_store4<SPLIT>(ra[i], sa + (r >> 3) * SBO + (r & 7) * 16 + poff, A_BYTES);
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const int n = sr + RSTEP * i;
+      if (n < n_tile) split_store4<SPLIT>(rw[i], sw + (n >> 3) * SBO + (n & 7) * 16 + poff, W_BYTES);
+    }
+    if (c + 1 < n_chunks) fetch(c + 1);
+    fence_async_smem();
+    mbar_arrive(bar + 3 + st);
   }
-  if (tid == 0) mma_commit(bar + 2);
-  mbar_wait(bar + 2, 0);
+  }   // staging warps
+  if (n_chunks > 0) mbar_wait(bar + 2, 0);
   fence_after_sync();
 
   // ---- epilogue: thread = row (TMEM lane quadrant warp & 3), the two warps of a quadrant alternate 16-column chunks ----
-  {
+  if (warp < STAGERS / 32) {
     const int row = (warp & 3) * 32 + lane, m = m0 + row;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* crow = g.C + bz * g.c_batch + (long long)m * g.ldc + n0;
