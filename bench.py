@@ -379,7 +379,9 @@ def main():
             # `frac` / `achieved`: the FLOPs this kernel itself executes (factored first Linear: W_r r per edge, 128x128 second
             # Linear, <q,k>) over its own live launch time
             'achieved': tf(f_min_k, k_ms), 'frac': tf(f_min_k, k_ms) / peak_tf, 'frac_executed': tf(f_min_k, k_ms) / peak_tf,
-            'traffic': (ncu_note('edge_k') or {}).get('dram_bytes_per_launch'),
+            # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture, scaled per edge
+            'traffic': ((ncu_note('edge_k') or {}).get('dram_bytes_per_edge') or 0) * E or None,
+            'traffic_source': (ncu_note('edge_k') or {}).get('source'),
             'tensor_active_ncu_pct': (ncu_note('edge_k') or {}).get('sm__pipe_tensor_cycles_active_pct'),
             'ms_per_launch': k_ms, 'launches_per_step': 16, 'share_of_step': 16 * k_ms / ms,
             'flops_per_launch_executed': f_min_k, 'flops_per_launch_ref_formulation': f_ref_k,
