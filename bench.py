@@ -332,6 +332,7 @@ def main():
     # ---- the path's only collective: one gather of the final states through the product's gather_results ----
     gather_ms = None
     if world > 1:
+        D.gather_results(sampler.pos, sampler.v, sizes_all)      # untimed: the first all_gather sets the communicator up
         barrier()
         t0 = time.perf_counter()
         full_pos, full_v = D.gather_results(sampler.pos, sampler.v, sizes_all)
