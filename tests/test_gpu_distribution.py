@@ -113,6 +113,74 @@ def test_final_distributions_indistinguishable(cuda_lib):
         assert p_dist > 0.01 and p_rocs > 0.01 and p_type > 0.01
 
 
+def _molecule_stats(pos, v, mol_ptr, ref, ref_ptr):
+    """Per-molecule statistics (independent samples, unlike the pooled pair distances of one coupled batch): radius of gyration,
+    mean pair distance, mean nearest-neighbour distance, shape Tanimoto; plus the atom-type histogram."""
+    pos, v = pos.cpu().double(), v.cpu()
+    rg, mp, nn = [], [], []
+    for m in range(len(mol_ptr) - 1):
+        p = pos[int(mol_ptr[m]):int(mol_ptr[m + 1])]
+        dm = (p[:, None] - p[None]).norm(dim=-1)
+        rg.append((p - p.mean(0)).pow(2).sum(1).mean().sqrt())
+        mp.append(dm[torch.triu(torch.ones_like(dm), 1) > 0].mean())
+        nn.append((dm + 1e9 * torch.eye(p.shape[0], dtype=dm.dtype)).min(1).values.mean())
+    return dict(rg=torch.stack(rg), pair=torch.stack(mp), nn=torch.stack(nn), rocs=orc.get_rocs_batch(pos.float(), mol_ptr, ref, ref_ptr),
+                types=torch.bincount(v.long(), minlength=15).double())
+
+
+def test_full_1000_step_population_vs_unmodified_reference(cuda_lib):
+    """The process the reference actually runs: 1000 reverse steps with train-mode BatchNorm, final state compared with
+    tests/golden/population.pt -- eight independent runs of the UNMODIFIED reference (tests/golden/make_population_golden.py).
+    Batch statistics couple the 48 molecules of a run (the run-level mean radius of gyration scatters by 0.1 .. 0.25 A between
+    runs, against 0.07 A if molecules were independent), so the RUN is the sampling unit: eight CUDA runs per arithmetic mode
+    (in-kernel Philox noise) against the eight reference runs, Mann-Whitney on the run-level means of every statistic, and the
+    pooled atom-type histogram.  Not distinguishable at the 1 % level = pass."""
+    from scipy import stats
+    from test_host_cpu import make_dropin
+    from test_gpu_parity import batch_of
+    import synth
+    from conftest import manifest_shapes
+    fx = torch.load(os.path.join(ROOT, 'tests', 'golden', 'population.pt'))
+    sizes, shape, steps = fx['sizes'], fx['shape'], fx['steps']
+    B, R = len(sizes), len(fx['runs'])
+    assert R >= 8
+    mol_ptr = orc.mol_ptr_from_sizes(sizes)
+    N = int(mol_ptr[-1])
+    g = torch.Generator().manual_seed(5)
+    ref = (1.5 * torch.randn(B * 20, 3, generator=g)).double()
+    ref_ptr = torch.arange(0, B * 20 + 1, 20)
+    keys = ('rg', 'pair', 'nn', 'rocs')
+
+    def run_level(pops):
+        return {k: torch.stack([p[k].mean() for p in pops]) for k in keys}, sum(p['types'] for p in pops)
+    assert all(bool(torch.isfinite(r['pos']).all()) for r in fx['runs'])
+    ref_runs, ref_types = run_level([_molecule_stats(r['pos'], r['v'], mol_ptr, ref, ref_ptr) for r in fx['runs']])
+    # the statistics can tell populations apart: the initial noise is not distributed like the final samples
+    init_runs, _ = run_level([_molecule_stats(r['pos0'], r['v0'], mol_ptr, ref, ref_ptr) for r in fx['runs']])
+    assert stats.mannwhitneyu(ref_runs['rg'].numpy(), init_runs['rg'].numpy()).pvalue < 1e-3
+    print('reference runs: ' + '  '.join('%s %.3f +- %.3f' % (k, float(ref_runs[k].mean()), float(ref_runs[k].std())) for k in keys))
+    sd = synth.synth_state_dict(manifest_shapes(), fx['seed'])
+    for precision in ('bf16x3', 'bf16'):
+        pops = []
+        for run in range(R):
+            m, _ = make_dropin(knn=fx['k'], num_diffusion_timesteps=steps)
+            m.load_state_dict(sd, strict=False)
+            m = m.cuda().train()
+            m.smb_precision, m.smb_noise, m.smb_seed, m.smb_keep_traj = precision, 'philox', 100 + run, False
+            gg = torch.Generator().manual_seed(700 + run)
+            pos1, v1 = torch.randn(N, 3, generator=gg), torch.randint(0, 15, (N,), generator=gg)
+            r = m.sample_diffusion(pos1.cuda(), v1.cuda(), batch_of(sizes), shape.view(-1, 3).cuda(), num_steps=steps, center_pos_mode='none')
+            assert torch.isfinite(r['pos']).all()
+            pops.append(_molecule_stats(r['pos'], r['v'], mol_ptr, ref, ref_ptr))
+        mine, my_types = run_level(pops)
+        pp = {k: stats.mannwhitneyu(mine[k].numpy(), ref_runs[k].numpy(), alternative='two-sided').pvalue for k in keys}
+        keep = (my_types + ref_types) > 0
+        pp['types'] = stats.chi2_contingency(torch.stack([my_types[keep], ref_types[keep]]).numpy())[1]
+        print('%s runs:      ' % precision + '  '.join('%s %.3f +- %.3f' % (k, float(mine[k].mean()), float(mine[k].std())) for k in keys)
+              + ' | p: ' + '  '.join('%s %.3f' % kv for kv in pp.items()))
+        assert min(pp.values()) > 0.01, (precision, pp)
+
+
 def test_stability_kernel_matches_reference(cuda_lib):
     from test_gpu_parity import build_model, batch_of
     from shapemol_b200.engine import BatchDesc

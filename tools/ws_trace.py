@@ -14,7 +14,7 @@ from conftest import load_golden  # noqa: E402
 from test_gpu_parity import build_model, batch_of  # noqa: E402
 from shapemol_b200 import _lib  # noqa: E402
 
-NAMES = ['P arrive', 'G1 issue', 'LN start', 'LN arrive', 'G2 issue', 'E2 start', 'E2 end', 'G1 a1full', 'G1 mma\'d', 'G1 commit', 'G1 a1free', 'G1 loaded', 'G1 dfree', 'P prewait', 'P postwait', 'CV qb', 'CV dmfull', 'CV bm', 'FOLD issue', '-']
+NAMES = ['P arrive', 'G1 issue', 'LN start', 'LN arrive', 'G2 issue', 'E2 start', 'E2 end', 'G1 a1full', 'G1 mma\'d', 'G1 commit', 'G1 a1free', 'G1 loaded', 'G1 dfree', 'P prewait', 'P postwait', 'CV qb', 'CV mfree', 'CV bm', 'CV folded', 'CV staged']
 
 
 def main():
@@ -42,7 +42,7 @@ def main():
     nt = int((buf[0] > 0).sum())
     t0 = buf[buf > 0].min()
     rel = np.where(buf > 0, buf - t0, -1)
-    order = [13, 14, 0, 7, 12, 1, 8, 9, 10, 11, 2, 3, 15, 18, 16, 17, 4, 5, 6]
+    order = [13, 14, 0, 7, 12, 1, 8, 9, 10, 11, 2, 3, 15, 19, 18, 16, 17, 4, 5, 6]
     print('tiles traced', nt)
     print('tile ' + ' '.join('%10s' % NAMES[e] for e in order))
     for i in list(range(0, 6)) + list(range(40, 48)):
@@ -50,7 +50,7 @@ def main():
             print('%4d ' % i + ' '.join('%10d' % rel[e][i] for e in order))
     a, b = 20, min(nt, 80) - 1
     print('mean period (tiles %d..%d):' % (a, b), ' '.join('%s %.0f' % (NAMES[e], (buf[e][b] - buf[e][a]) / (b - a)) for e in order))
-    for (x, y) in ((1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (15, 18), (18, 16), (16, 17), (17, 4), (13, 14), (14, 0), (0, 13), (0, 1), (7, 12), (12, 1), (1, 8), (8, 9), (9, 10), (10, 11)):
+    for (x, y) in ((1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (15, 19), (19, 18), (18, 16), (17, 15), (16, 17), (17, 4), (13, 14), (14, 0), (0, 13), (0, 1), (7, 12), (12, 1), (1, 8), (8, 9), (9, 10), (10, 11)):
         if buf[x][a:b].min() <= 0 or buf[y][a:b].min() <= 0:
             continue
         d = (buf[y][a:b] - buf[x][a:b])
