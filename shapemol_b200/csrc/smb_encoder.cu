@@ -37,7 +37,7 @@ constexpr float VN_EPS = 1e-6f;  // EPS of models/shape_vn_layers.py:6
 constexpr int STAT_CTAS = 148 * 8;
 
 struct Ws {
-  size_t xx, idx, h0, hc, uv, pc, w4, wc, part, bnp, gram, total;
+  size_t xx, idx, h0, hc, uv, pc, w4, wc, part, bnp, gram, wimg, wimg_bytes, total;
 };
 constexpr int GRAM_MAX_P = 1024;   // clouds up to this size take the tensor-core Gram path (the top-k holds a row in registers)
 
@@ -57,6 +57,12 @@ static Ws plan(int n_blocks, int latent, int k, size_t n_points, int P) {
   w.part = take((size_t)STAT_CTAS * 2 * HS * 8);
   w.bnp = take(2 * HS * 4);
   w.gram = take(P <= GRAM_MAX_P ? n_points * (size_t)P * 4 : 0);   // [B][P][P] fp32
+  {   // pre-split weight image of the node GEMM in flight (smb_tc_gemm.cu)
+    const int k_blk[1] = {HS}, k_c[1] = {HS * n_blocks};
+    const long long a = tc_gemm_w_img_bytes(UVW, k_blk, 1, true), b = tc_gemm_w_img_bytes(PCW, k_c, 1, true);
+    w.wimg_bytes = (size_t)(a > b ? a : b);
+    w.wimg = take(w.wimg_bytes);
+  }
   w.total = o;
   return w;
 }
@@ -172,12 +178,14 @@ __global__ void __launch_bounds__(256) enc_knn_kernel(const float* __restrict__ 
 }
 
 // ---- node GEMM: C[M][ldc](N) = A[M][lda](K) * W[N][ldw](K)^T on tcgen05 (split-bf16 products, smb_tc_gemm.cu) ----------
-static int enc_gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, size_t M, int N, int K, cudaStream_t st) {
+static int enc_gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, size_t M, int N, int K, void* wimg, size_t wimg_bytes,
+                    cudaStream_t st) {
   TcGemmArgs g;
   memset(&g, 0, sizeof(g));
   g.seg[0].a = A; g.seg[0].lda = lda; g.seg[0].k = K;
   g.n_segs = 1; g.W = W; g.ldw = ldw; g.M = (int)M; g.N = N; g.C = C; g.ldc = ldc;
   g.split3 = 1;   // fp32-level products: the next layer's kNN graph is selected on these features
+  g.w_img = wimg; g.w_img_bytes = (long long)wimg_bytes;
   return launch_tc_gemm(g, 1, st);
 }
 
@@ -529,6 +537,7 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
   double* part = reinterpret_cast<double*>(base + L.part);
   float* bnp = reinterpret_cast<float*>(base + L.bnp);
   float* gram = P <= GRAM_MAX_P ? reinterpret_cast<float*>(base + L.gram) : nullptr;
+  void* wimg = base + L.wimg;
   const int stat_grid = (int)(n_points < (size_t)STAT_CTAS ? n_points : (size_t)STAT_CTAS);
   const double edge_count = (double)n_points * (double)k;
 
@@ -547,7 +556,7 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
     const int ldi = i == 0 ? HS : HC;
     ENC_LAUNCH(launch_knn(in, (size_t)3 * ldi, 3, HS, ldi, xx, B, P, k, idx, gram, st));
     ENC_KERNEL(enc_prep_w4_kernel<<<(HS * HS + 255) / 256, 256, 0, st>>>(w.block_feat[i], w.block_dir[i], HS, w4));
-    ENC_LAUNCH(enc_gemm(in, ldi, w4, HS, uv, UVW, n_rows, UVW, HS, st));
+    ENC_LAUNCH(enc_gemm(in, ldi, w4, HS, uv, UVW, n_rows, UVW, HS, wimg, L.wimg_bytes, st));
     ENC_KERNEL(enc_edge_stats_kernel<<<stat_grid, HS, 0, st>>>(uv, idx, P, k, n_points, part));
     ENC_KERNEL(enc_bn_final_kernel<<<1, HS, 0, st>>>(part, stat_grid, HS, edge_count, 1, w.block_bn_w[i], w.block_bn_b[i],
                                                      w.block_bn_rm[i], w.block_bn_rv[i], bnp));
@@ -558,7 +567,7 @@ static int encode(const smb_encoder_weights& w, const float* clouds, int B, int 
   SMB_CUDA_OK(cudaMemsetAsync(wc, 0, (size_t)PCW * HC * 4, st));
   SMB_CUDA_OK(cudaMemcpyAsync(wc, w.conv_c_feat, (size_t)w.latent * HC * 4, cudaMemcpyDeviceToDevice, st));
   SMB_CUDA_OK(cudaMemcpyAsync(wc + (size_t)w.latent * HC, w.conv_c_dir, (size_t)HC * 4, cudaMemcpyDeviceToDevice, st));
-  ENC_LAUNCH(enc_gemm(hc, HC, wc, HC, pc, PCW, n_rows, w.latent + 1, HC, st));
+  ENC_LAUNCH(enc_gemm(hc, HC, wc, HC, pc, PCW, n_rows, w.latent + 1, HC, wimg, L.wimg_bytes, st));
   const int c_grid = (int)((n_points + 7) / 8 < (size_t)STAT_CTAS ? (n_points + 7) / 8 : (size_t)STAT_CTAS);
   ENC_KERNEL(enc_c_stats_kernel<<<c_grid, 256, 0, st>>>(pc, w.latent, n_points, part));
   ENC_KERNEL(enc_bn_final_kernel<<<1, HS, 0, st>>>(part, c_grid, w.latent, (double)n_points, w.training, w.conv_c_bn_w, w.conv_c_bn_b,

@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(128) xv_vn_kernel(const float* __restrict__ al
 
 // C[M x N] (+)= A[rows gathered by a_idx][K] . W[N][K]^T (+ bias): the tcgen05 split-bf16 GEMM (smb_tc_gemm.cu)
 struct Seg { const float* a; const int* idx; int lda; int k; };
+// scratch for the pre-split weight image of the GEMM in flight: part of the calling forward's workspace (stream-ordered reuse)
+thread_local void* t_wimg = nullptr;
+thread_local long long t_wimg_bytes = 0;
 int gemm_cat(const Seg* segs, int n_segs, const float* W, int ldw, int M, int N, const float* bias, bool accumulate, float* C, int ldc,
              cudaStream_t st) {
   TcGemmArgs g;
@@ -181,6 +184,7 @@ int gemm_cat(const Seg* segs, int n_segs, const float* W, int ldw, int M, int N,
     off += segs[s].k;
   }
   g.n_segs = n_segs; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.bias = bias; g.accumulate = accumulate ? 1 : 0; g.C = C; g.ldc = ldc;
+  g.w_img = t_wimg; g.w_img_bytes = t_wimg_bytes;
   return launch_tc_gemm(g, 1, st);
 }
 int gemm(const float* A, const int* a_idx, int lda, const float* W, int ldw, int M, int N, int K, const float* bias, bool accumulate,
@@ -254,6 +258,8 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
   auto P = [&](const std::string& n) { return reinterpret_cast<const float*>(base + raw_weight_offset(d, n)); };
   auto wsf = [&](size_t off) { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws_base) + off); };
   auto wsi = [&](size_t off) { return reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws_base) + off); };
+  t_wimg = reinterpret_cast<unsigned char*>(ws_base) + W.g_wimg;
+  t_wimg_bytes = (long long)W.g_wimg_bytes;
   float* x = wsf(W.x);
   float* inv = wsf(W.inv);
   const int* nbr = wsi(W.nbr);

@@ -9,6 +9,8 @@
 #include "smb_common.cuh"
 #include "smb_layout.h"
 
+namespace smb { long long tc_gemm_w_img_bytes(int N, const int* seg_k, int n_segs, bool split3); }   // smb_tc_gemm.cu
+
 namespace smb {
 
 static thread_local char g_err[512] = "";
@@ -150,6 +152,11 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
     w.g_hid = c.take(m * H * 4); w.g_out = c.take(m * H * 4); w.g_alpha = c.take(m * kHeads * 4);
     w.g_rbf = c.take(m * kRbf * 4); w.g_rel = c.take(m * 3 * 4); w.g_idx = c.take(3 * m * 4);
     w.g_node = c.take(n * H * 4); w.g_bn = c.take(n * 32 * 4);
+    {
+      const int seg_k[4] = {kRbf, H, H, kShape};
+      w.g_wimg_bytes = (size_t)tc_gemm_w_img_bytes(H, seg_k, 4, false);
+      w.g_wimg = c.take(w.g_wimg_bytes);
+    }
   }
   w.tiles = c.take(16 + (size_t)w.max_tiles * 16);
   w.total = c.off;

@@ -162,7 +162,13 @@ struct TcGemmArgs {
   long long a_batch, w_batch, c_batch, idx_batch;   // element strides between the grid.z batches (0: shared)
   int split3;          // three bf16 pieces per operand (fp32-level products, six MMAs per step) instead of two
   int vec, vec_c;      // set by the launcher: 16-byte aligned operand / output rows
+  // optional scratch for the pre-split image of W (shared weights only, w_batch == 0): a small kernel splits W once per launch
+  // and the GEMM's CTAs bulk-copy its chunks instead of each re-splitting the same tile; NULL / too small: in-kernel staging
+  void* w_img;
+  long long w_img_bytes;
+  int use_img;         // set by the launcher
 };
+long long tc_gemm_w_img_bytes(int N, const int* seg_k, int n_segs, bool split3);   // scratch needed for TcGemmArgs::w_img
 int launch_tc_gemm(const TcGemmArgs& g, int n_batch, cudaStream_t st);
 
 // generic-shape fp32 path (smb_generic.cu): hidden_dim != 128

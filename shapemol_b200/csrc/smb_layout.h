@@ -132,6 +132,7 @@ struct Workspace {
   size_t g_rbf, g_rel;     // [M][20], [M][3]
   size_t g_idx;            // int32 [3][M]: destination / source atom, molecule (-1: empty slot)
   size_t g_node, g_bn;     // [N][H], [N][32]
+  size_t g_wimg, g_wimg_bytes;   // pre-split weight image of the GEMM in flight (smb_tc_gemm.cu)
   size_t tiles;     // [max_tiles] int4 tile descriptors, preceded by the tile count (16 bytes)
   int max_tiles;    // N/4 + B + 8: a tile holds >= 4 destination atoms unless it is the last of its molecule
   int bn_part_rows;

@@ -85,6 +85,35 @@ __device__ __forceinline__ float4 load4(const float* p, int k, int kmax, bool ve
   return x;
 }
 
+// chunk c of the concatenated K range -> (segment, first k inside it)
+__device__ __forceinline__ void chunk_of(const TcGemmArgs& g, int c, int KC, int& s, int& k0) {
+  s = 0; k0 = c * KC;
+  while (k0 >= g.seg[s].k) { k0 -= (g.seg[s].k + KC - 1) / KC * KC; ++s; }
+}
+
+// Pre-split image of a shared W: for every (column tile j, chunk c) the SPLIT x [256 n][KC k] bf16 K-major blocks exactly as a
+// pipeline stage holds them, so that a CTA fetches a chunk of W with ONE bulk copy.  grid = (chunks, column tiles), 256 threads.
+template <int SPLIT>
+__global__ void __launch_bounds__(256) tc_wsplit_kernel(TcGemmArgs g, int n_chunks) {
+  using C = Cfg<SPLIT>;
+  constexpr int KC = C::KC, W_BYTES = C::W_BYTES, SBO = C::SBO;
+  const int c = blockIdx.x, n0 = blockIdx.y * NT_MAX;
+  int s, k0;
+  chunk_of(g, c, KC, s, k0);
+  const TcGemmSeg& sg = g.seg[s];
+  unsigned char* dst = reinterpret_cast<unsigned char*>(g.w_img) + ((size_t)blockIdx.y * n_chunks + c) * (SPLIT * W_BYTES);
+  for (int it = threadIdx.x; it < NT_MAX * (KC / 8); it += 256) {
+    const int n = it / (KC / 8), kg = it % (KC / 8);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + kg * 8 + e;
+      v[e] = (n0 + n < g.N && k < sg.k) ? __ldg(g.W + (long long)(n0 + n) * g.ldw + sg.w_off + k) : 0.f;
+    }
+    split_store<SPLIT>(v, dst + (n >> 3) * SBO + kg * 128 + (n & 7) * 16, W_BYTES);
+  }
+}
+
 template <int SPLIT>
 __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   using C = Cfg<SPLIT>;
@@ -148,9 +177,10 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   } else {
 
   float4 ra[NA], rw[NW];                // this thread's pieces of the staged chunk (fp32)
+  const bool img = g.use_img != 0;      // W arrives pre-split through bulk copies
   auto fetch = [&](int c) {             // chunk c -> (segment, k0)
-    int s = 0, k0 = c * KC;
-    while (k0 >= g.seg[s].k) { k0 -= (g.seg[s].k + KC - 1) / KC * KC; ++s; }
+    int s, k0;
+    chunk_of(g, c, KC, s, k0);
     const TcGemmSeg& sg = g.seg[s];
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
@@ -159,6 +189,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
       if (m < g.M) arow = sg.idx ? (long long)__ldg(sg.idx + bz * g.idx_batch + m) : (long long)m;
       ra[i] = arow >= 0 ? load4(sg.a + bz * g.a_batch + arow * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (img) return;
     const float* wb = g.W + bz * g.w_batch + sg.w_off;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
@@ -174,15 +205,22 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
     unsigned char* sa = stages + st * STAGE_BYTES;     // A pieces, then W pieces
     unsigned char* sw = sa + SPLIT * A_BYTES;
     if (c >= 2) mbar_wait(bar + st, ((c >> 1) - 1) & 1);   // the MMAs of chunk c - 2 have read this stage
+    if (img && tid == 0) {
+      mbar_expect_tx(bar + 3 + st, SPLIT * W_BYTES);
+      bulk_g2s(sw, reinterpret_cast<const unsigned char*>(g.w_img) + ((size_t)blockIdx.y * n_chunks + c) * (SPLIT * W_BYTES), SPLIT * W_BYTES,
+               bar + 3 + st);
+    }
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int r = sr + RSTEP * i;
       split_store4<SPLIT>(ra[i], sa + (r >> 3) * SBO + (r & 7) * 16 + poff, A_BYTES);
     }
+    if (!img) {
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int n = sr + RSTEP * i;
-      if (n < n_tile) split_store4<SPLIT>(rw[i], sw + (n >> 3) * SBO + (n & 7) * 16 + poff, W_BYTES);
+      for (int i = 0; i < NW; ++i) {
+        const int n = sr + RSTEP * i;
+        if (n < n_tile) split_store4<SPLIT>(rw[i], sw + (n >> 3) * SBO + (n & 7) * 16 + poff, W_BYTES);
+      }
     }
     if (c + 1 < n_chunks) fetch(c + 1);
     fence_async_smem();
@@ -233,6 +271,13 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+long long tc_gemm_w_img_bytes(int N, const int* seg_k, int n_segs, bool split3) {
+  const int KC = split3 ? Cfg<3>::KC : Cfg<2>::KC;
+  long long chunks = 0;
+  for (int s = 0; s < n_segs; ++s) chunks += (seg_k[s] + KC - 1) / KC;
+  return (long long)((N + NT_MAX - 1) / NT_MAX) * chunks * (split3 ? 3 * Cfg<3>::W_BYTES : 2 * Cfg<2>::W_BYTES);
+}
+
 int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
   if (g_in.M <= 0 || g_in.N <= 0 || n_batch <= 0) return 0;
   if (g_in.n_segs < 1 || g_in.n_segs > 4) { set_error_msg("tc_gemm: 1..4 operand segments"); return SMB_E_BADARG; }
@@ -244,6 +289,20 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
   g.vec = vec ? 1 : 0;
   g.vec_c = (aligned16(g.C) && g.ldc % 4 == 0 && g.c_batch % 4 == 0) ? 1 : 0;
   const dim3 grid((unsigned)((g.M + TM - 1) / TM), (unsigned)((g.N + NT_MAX - 1) / NT_MAX), (unsigned)n_batch);
+  {
+    int seg_k[4];
+    for (int s = 0; s < g.n_segs; ++s) seg_k[s] = g.seg[s].k;
+    const long long need = tc_gemm_w_img_bytes(g.N, seg_k, g.n_segs, g.split3 != 0);
+    g.use_img = (g.w_img && g.w_batch == 0 && need <= g.w_img_bytes && (reinterpret_cast<uintptr_t>(g.w_img) & 127) == 0) ? 1 : 0;
+    if (g.use_img) {
+      const int KC = g.split3 ? Cfg<3>::KC : Cfg<2>::KC;
+      int n_chunks = 0;
+      for (int s = 0; s < g.n_segs; ++s) n_chunks += (g.seg[s].k + KC - 1) / KC;
+      const dim3 sgrid((unsigned)n_chunks, grid.y);
+      if (g.split3) tc_wsplit_kernel<3><<<sgrid, 256, 0, st>>>(g, n_chunks);
+      else tc_wsplit_kernel<2><<<sgrid, 256, 0, st>>>(g, n_chunks);
+    }
+  }
   if (g.split3) {
     static size_t configured[kMaxDevices] = {};
     if (int rc = ensure_dynamic_smem(tc_gemm_kernel<3>, Cfg<3>::SMEM_TOTAL, configured)) return rc;
