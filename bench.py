@@ -83,13 +83,34 @@ def make_workload(n_shapes, per_shape, seed, fixed_atoms=0):
     return sizes, batch, pos, v, shape
 
 
-def tiles_and_rows(sizes, k):
-    """Static tile list of the edge pipeline (csrc/smb_edge_ws.cu tiles_of): 128-row tiles of whole destinations of one
-    molecule.  Returns (tiles, edge rows)."""
-    deg = torch.clamp(sizes - 1, max=k)
-    per = torch.where(deg > 0, torch.clamp(128 // torch.clamp(deg, min=1), max=8), torch.ones_like(deg))
-    tiles = torch.where(deg > 0, (sizes + per - 1) // per, torch.ones_like(sizes))
-    return int(tiles.sum()), int((sizes * deg).sum())
+def tiles_and_rows(sizes, k, split=None):
+    """Static tile list of the edge pipeline (csrc/smb_edge_ws.cu TileWalk): <= 128 consecutive edge slots of one molecule, at
+    most 8 destinations touched; split (default, SMB_TILE_SPLIT != 0): runs of about E / ceil(E / 128) slots that may begin and
+    end inside a destination, else whole destinations.  Returns (tiles, edge rows)."""
+    if split is None:
+        split = os.environ.get('SMB_TILE_SPLIT', '1') != '0'
+    cache, tiles, rows = {}, 0, 0
+    for n in sizes.tolist():
+        if n not in cache:
+            deg = min(k, n - 1)
+            if deg <= 0:
+                cache[n] = (1 if n > 0 else 0, 0)
+            else:
+                E = n * deg
+                nt = (E + 127) // 128
+                target = (E + nt - 1) // nt if split else min(128 // deg, 8) * deg
+                e, cnt = 0, 0
+                while e < E:
+                    r = min(target, E - e)
+                    d0 = e // deg
+                    if (e + r - 1) // deg - d0 + 1 > 8:
+                        r = (d0 + 8) * deg - e
+                    e += r
+                    cnt += 1
+                cache[n] = (cnt, E)
+        tiles += cache[n][0]
+        rows += cache[n][1]
+    return tiles, rows
 
 
 def build_model(k, precision):

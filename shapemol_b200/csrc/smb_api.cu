@@ -110,7 +110,14 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   const bool node_tc5 = ws && node_tc5_supported(d, n_max);
   int4* tiles = wptr<int4>(ws_base, W.tiles + 16);
   int* n_tiles = wptr<int>(ws_base, W.tiles);
-  if (ws && !io.reuse_static) SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, tiles, n_tiles, st));
+  // two static tile lists: whole destinations per tile for the X2H block (ROLE_V's epilogue pays for every extra part of a tile),
+  // runs that may begin / end inside a destination -- fewer, fuller tiles -- for the gate and the H2X block
+  int4* tiles_s = wptr<int4>(ws_base, W.tiles_s + 16);
+  int* n_tiles_s = wptr<int>(ws_base, W.tiles_s);
+  if (ws && !io.reuse_static) {
+    SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, false, tiles, n_tiles, st));
+    SMB_LAUNCH(launch_build_tiles(b.mol_ptr, B, d.k, true, tiles_s, n_tiles_s, st));
+  }
   auto edge = [&](int role, const EdgeArgs& e, int* bn_rows) -> int {
     return ws ? launch_edge_ws(role, e, bn_rows, st) : launch_edge(d, role, e, bn_rows, st);
   };
@@ -125,6 +132,7 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
   {  // global edge gate, computed once from the input coordinates (uni_transformer.py:507)
     EdgeArgs e = eb;
     fill_edge_weights(e, blob, L.gate);
+    e.tiles = tiles_s; e.n_tiles = n_tiles_s;
     SMB_TIMED(SMB_PROF_GATE, edge(ROLE_GATE, e, nullptr));
   }
 
@@ -187,6 +195,8 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       EdgeArgs e = eb;
       e.col_a = 0; e.col_b = H;
       fill_edge_weights(e, blob, y.xk);
+      e.tiles = tiles_s; e.n_tiles = n_tiles_s;
+      e.zero_ptr = vn; e.zero_stride = kVnRow; e.zero_off = 3; e.zero_len = 3 * kHeads;   // ... ROLE_XV: the o sums in the vn row
       SMB_TIMED(SMB_PROF_EDGE_K, edge(ROLE_K, e, nullptr));
     }
     int bn_rows = 0;
@@ -196,7 +206,9 @@ static int forward_impl(const smb_model_dims& d, const void* blob, const smb_bat
       e.vn_feat = fptr(blob, y.vn_feat); e.vn_dir = fptr(blob, y.vn_dir);
       e.vn_shape = vn_shape + (size_t)l * (B > 0 ? B : 1) * 96;
       fill_edge_weights(e, blob, y.xv);
+      e.tiles = tiles_s; e.n_tiles = n_tiles_s;
       SMB_TIMED(SMB_PROF_EDGE_XV, edge(ROLE_XV, e, &bn_rows));
+      if (ws) SMB_LAUNCH(launch_xv_split_finish(e, bn_rows, &bn_rows, st));
     }
     {
       BnArgs bn;

@@ -134,19 +134,21 @@ struct Plan {
   static constexpr int w2_bytes = ROLE == ROLE_GATE ? 0 : ROLE == ROLE_XV ? kHeads * H * 2 : H * H * 2;
   static constexpr int o_a1 = o_w2 + w2_bytes;    // 2 slots
   static constexpr int o_ab = o_a1 + 2 * A1_BYTES;   // 3 slots
-  static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float2[2 buffers][2 halves][128]
-  static constexpr int o_z = o_stat + 4096;          // ROLE_V: z^T operand, 2 x 32768
+  static constexpr int o_stat = o_ab + 3 * AB_BYTES; // LN: float[2 buffers][2 halves][128]
+  static constexpr int o_z = o_stat + 2048;          // ROLE_V: z^T operand, 2 x 32768
   static constexpr int o_e2 = o_z + (ROLE == ROLE_V ? 2 * TM * H * 2 : 0);
   // E2 scratch, one per group.  ROLE_V / ROLE_XV: one staging slot (the tile's alpha block; ROLE_XV: + shape float[96]), then
   // role scratch.  ROLE_K: logits float[128][17] | gate float[128]
   static constexpr int alpha_bytes = kAlphaTileFloats * 4;
-  static constexpr int stage_bytes = ROLE == ROLE_K ? 0 : ROLE == ROLE_XV ? alpha_bytes + 384 : alpha_bytes;
+  static constexpr int o_nbst = ROLE == ROLE_XV ? alpha_bytes + 384 : alpha_bytes;   // neighbour tiles' split statistics: 2 x 32 floats
+  static constexpr int stage_bytes = ROLE == ROLE_K ? 0 : o_nbst + 256;
   static constexpr int e_stage = 0;
-  static constexpr int e_log = stage_bytes;           // ROLE_K logits / ROLE_XV w : float[128][17]
+  static constexpr int e_ptab = stage_bytes;          // int4[NDMAX]: first row, row count, alpha offset of the tile's parts
+  static constexpr int e_log = e_ptab + 128;          // ROLE_K logits / ROLE_XV w : float[128][17]
   static constexpr int e_ew = e_log + 8704;           // ROLE_K float[128]
   static constexpr int e_rel = e_log + 8704;          // ROLE_XV float4[128]
   static constexpr int e_o = e_rel + 2048;            // ROLE_XV float[8][16][4]
-  static constexpr int e2_bytes = ROLE == ROLE_K ? e_ew + 512 : ROLE == ROLE_V ? stage_bytes : e_o + 2048;
+  static constexpr int e2_bytes = ROLE == ROLE_K ? e_ew + 512 : ROLE == ROLE_V ? e_log : e_o + 2048;
   static constexpr int NGP = ROLE == ROLE_XV ? 4 : 2;
   static constexpr int o_vnw = o_e2 + NGP * e2_bytes;     // ROLE_XV: vn_feat | vn_dir
   static constexpr int o_bn = o_vnw + (ROLE == ROLE_XV ? 2 * kHeads * kVnStride * 4 : 0);   // ROLE_XV: float[16 E2 warps][32] BatchNorm partial sums
@@ -199,13 +201,29 @@ __device__ __forceinline__ void rbf20(float dist, float (&e)[20]) {
   }
 }
 
+// Tile = `nrows` <= 128 consecutive edge slots of ONE molecule (slot e = destination * deg + neighbour): it starts `s0` slots into
+// destination d0 and touches nd <= NDMAX destinations ("parts"); the first and the last part may be incomplete -- the rest of
+// such a destination is the last / first part of the neighbouring tile.
+//   int4 = { first atom of the molecule, molecule | s0 << 24, n | d0 << 8 | nd << 16 | deg << 24, (65536 / deg + 1) | nrows << 20 }
 struct Tile {
-  int a0, mol, n, d0, nd, deg;
+  int a0, mol, n, d0, nd, deg, s0, nrows;
   uint32_t recip;
   __device__ __forceinline__ explicit Tile(const int4& t)
-      : a0(t.x), mol(t.y), n(t.z & 0xff), d0((t.z >> 8) & 0xff), nd((t.z >> 16) & 0xff), deg((t.z >> 24) & 0xff), recip((uint32_t)t.w) {}
-  __device__ __forceinline__ int rows() const { return nd * deg; }
-  __device__ __forceinline__ int dst_of(int r) const { return (int)(((uint32_t)r * recip) >> 16); }   // r / deg for r < 128
+      : a0(t.x), mol(t.y & 0xffffff), n(t.z & 0xff), d0((t.z >> 8) & 0xff), nd((t.z >> 16) & 0xff), deg((t.z >> 24) & 0xff),
+        s0((t.y >> 24) & 0xff), nrows((t.w >> 20) & 0xff), recip((uint32_t)t.w & 0xfffffu) {}
+  __device__ __forceinline__ int rows() const { return nrows; }
+  __device__ __forceinline__ int dst_of(int r) const { return (int)(((uint32_t)(r + s0) * recip) >> 16); }   // part of row r < 128
+  __device__ __forceinline__ int slot_of(int r, int pd) const { return r + s0 - pd * deg; }                   // its neighbour slot
+  __device__ __forceinline__ int first(int pd) const { return max(pd * deg - s0, 0); }                        // first row of part pd
+  __device__ __forceinline__ int count(int pd) const { return min((pd + 1) * deg - s0, nrows) - first(pd); }
+  __device__ __forceinline__ bool head_split() const { return s0 > 0; }
+  __device__ __forceinline__ bool tail_split() const { return s0 + nrows < nd * deg; }
+  // alpha block: part pd starts at float aoff(pd) of a head's hstride() floats (smb_layout.h)
+  __device__ __forceinline__ int aoff(int pd) const { return pd == 0 ? 0 : ((count(0) + 3) & ~3) + (pd - 1) * ((deg + 3) & ~3); }
+  __device__ __forceinline__ int hstride() const {
+    const int h = aoff(nd - 1) + ((count(nd - 1) + 3) & ~3);
+    return h + ((4 - h) & 15);   // 4 mod 16: conflict-free 16-byte reads of four heads (ROLE_V)
+  }
 };
 
 // timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       for (int u = 0; u < P_ROWS; ++u) {
         const int r = min(ptid + u * (P_WARPS * 32), last);
         const int il = N.dst_of(r);
-        j[u] = __ldg(a.nbr + (size_t)(N.a0 + N.d0 + il) * KSTR + (r - il * N.deg));   // consumed an iteration later (-1 only in a single-atom molecule)
+        j[u] = __ldg(a.nbr + (size_t)(N.a0 + N.d0 + il) * KSTR + N.slot_of(r, il));   // consumed an iteration later (-1 only in a single-atom molecule)
       }
     };
     auto fetch_x = [&](const Tile& N, const int (&j)[P_ROWS]) {
@@ -463,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           const Tile T(__ldg(tiles + t));
           if (r < T.rows()) {
             const int dl = T.dst_of(r);
-            a.ew_out[(size_t)(T.a0 + T.d0 + dl) * KSTR + (r - dl * T.deg)] = 1.f / (1.f + __expf(-(dot + sd[TM + r] + s_b2[0])));
+            a.ew_out[(size_t)(T.a0 + T.d0 + dl) * KSTR + T.slot_of(r, dl)] = 1.f / (1.f + __expf(-(dot + sd[TM + r] + s_b2[0])));
           }
         }
         continue;
@@ -587,11 +605,18 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
     // what tile `t` needs from global memory, fetched after the group's previous tile: the tile's alpha block / shape
     // (cp.async) and this thread's gate value / relative position (registers)
+    // BOTH (off): both groups of ROLE_V work on every tile (a tile's parts are read in rounds of two; round rd belongs to group
+    // rd & 1; the two staging slots form a ring over the tiles, filled two tiles ahead by all 256 threads).  It halves the
+    // accumulator's hold time but the groups' throughput drops from 1.5 to 2 rounds per five-part tile: measured slower.
+    constexpr bool BOTH = false;
+    const int t_step = BOTH ? 1 : NG;
+    const int sid = BOTH ? e2w * 32 + lane : tg, sn = BOTH ? 2 * E2_GRP_THREADS : E2_GRP_THREADS;   // staging thread index / count
+    const int sync_id = BOTH ? BAR_E2 : bar_id;
     float pre_ew = 0.f, pre_x = 0.f, pre_y = 0.f, pre_z = 0.f;
     auto stage = [&](int t, const Tile& T) {
-      unsigned char* slot = es + P::e_stage;
-      const int dl = min(T.dst_of(r), NDMAX - 1), sl = r - dl * T.deg;
+      unsigned char* slot = BOTH ? smem + P::o_e2 + (t & 1) * P::e2_bytes + P::e_stage : es + P::e_stage;
       const bool valid = r < T.rows();
+      const int dl = valid ? T.dst_of(r) : 0, sl = T.slot_of(r, dl);
       if (ROLE == ROLE_K) {
         pre_ew = 0.f;
         if (valid) pre_ew = __ldg(a.ew_in + (size_t)(T.a0 + T.d0 + dl) * KSTR + sl);
@@ -599,7 +624,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         const float* src = a.alpha_t + (size_t)(t_begin + t) * kAlphaTileFloats;
         float* dst = reinterpret_cast<float*>(slot);
 #pragma unroll
-        for (int p = tg; p < kAlphaTileFloats / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        for (int p = sid; p < 4 * T.hstride(); p += sn) cp_async16(dst + p * 4, src + p * 4);   // 16 heads x hstride floats
+        if (sid < (kAlphaTileFloats - kAlphaSumOff) / 4) cp_async16(dst + kAlphaSumOff + sid * 4, src + kAlphaSumOff + sid * 4);   // sums | split statistics
+        // statistics of the other part of a split destination: the previous tile's last part | the next tile's first part
+        // (read only when this tile's first / last part is incomplete, which implies that the neighbour exists)
+        if (ROLE != ROLE_V && sid >= sn - 16) {
+          const int q = sid - (sn - 16), w = q >> 3;
+          if (w ? T.tail_split() : T.head_split())
+            cp_async16(slot + P::o_nbst + q * 16, a.alpha_t + (size_t)(t_begin + t + (w ? 1 : -1)) * kAlphaTileFloats + kAlphaSplitOff + (w ? 0 : 32) + (q & 7) * 4);
+        }
       }
       if (ROLE == ROLE_XV) {
         if (tg < 2 * kHeads * 3 / 4) cp_async16(slot + P::alpha_bytes + tg * 16, a.vn_shape + (size_t)T.mol * (2 * kHeads * 3) + tg * 4);
@@ -615,40 +648,65 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     };
 
     const int4 zero4 = make_int4(0, 0, 0, 0);
-    int4 td_cur = g < nt ? __ldg(tiles + g) : zero4;
-    int4 td_nx = g + NG < nt ? __ldg(tiles + g + NG) : zero4;
-    if (g < nt) stage(g, Tile(td_cur));
+    const int t_first = BOTH ? 0 : g;
+    int4 td_cur = t_first < nt ? __ldg(tiles + t_first) : zero4;
+    int4 td_nx = t_first + t_step < nt ? __ldg(tiles + t_first + t_step) : zero4;
+    if (t_first < nt) stage(t_first, Tile(td_cur));
     cp_async_commit();
+    if (BOTH) {
+      if (1 < nt) stage(1, Tile(td_nx));
+      cp_async_commit();
+    }
 #pragma unroll 1
-    for (int t = g; t < nt; t += NG) {
+    for (int t = t_first; t < nt; t += t_step) {
       const Tile T(td_cur);
       const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
       td_cur = td_nx;
-      if (t + 2 * NG < nt) td_nx = __ldg(tiles + t + 2 * NG);
+      if (t + 2 * t_step < nt) td_nx = __ldg(tiles + t + 2 * t_step);
       if (ROLE == ROLE_K && t + NG < nt) stage(t + NG, Tile(td_cur));   // registers only: the next tile's gate value
-      if (ROLE != ROLE_K && t + NG < nt && tg < (kAlphaTileFloats * 4 + 127) / 128) {
+      if (ROLE != ROLE_K && !BOTH && t + NG < nt && tg < (kAlphaTileFloats * 4 + 127) / 128) {
         // the staging slot is busy until this tile is done: pull the group's next alpha block into L2 meanwhile, so that
         // the cp.async issued after the trailing barrier does not pay the DRAM latency
         const float* nxt = a.alpha_t + (size_t)(t_begin + t + NG) * kAlphaTileFloats + tg * 32;
         if (!SMB_DBG(a, 32)) asm volatile("prefetch.L2 [%0];" :: "l"(nxt));
+        // ... and the split statistics of that tile's neighbours (the 128-byte line of the previous tile's last part / the next
+        // tile's first part), when it begins / ends inside a destination
+        if (ROLE != ROLE_V && tg < 2) {
+          const Tile N(td_cur);
+          if (tg ? N.tail_split() : N.head_split())
+            asm volatile("prefetch.L2 [%0];" :: "l"(a.alpha_t + (size_t)(t_begin + t + NG + (tg ? 1 : -1)) * kAlphaTileFloats + kAlphaSplitOff + (tg ? 0 : 32)));
+        }
       }
       const int b3 = t % ND2, bb = t % NB2;   // TMEM buffer / barrier slot
       const uint32_t dcol = R::D2_COL + (uint32_t)b3 * R::D2_STRIDE;
       const int rows = T.rows();
       const bool valid = r < rows;
-      const int dl = min(T.dst_of(r), NDMAX - 1);
-      const int SL = (T.deg + 3) & ~3;        // alpha slots per (head, destination)
-      const unsigned char* slot = es + P::e_stage;
-      const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV: [16][nd][SL] | sums [16][8]
+      const int dl = valid ? T.dst_of(r) : 0;
+      const int hs = T.hstride();             // alpha floats per head
+      const unsigned char* slot = BOTH ? smem + P::o_e2 + (t & 1) * P::e2_bytes + P::e_stage : es + P::e_stage;
+      const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV: the tile's alpha block
+      const float* s_nb = reinterpret_cast<const float*>(slot + P::o_nbst);   // neighbours' split statistics [prev last | next first][16][2]
+      // factor that turns the unnormalised alpha of an incomplete part into the destination's softmax: this part's (max, sum)
+      // and the other part's, from the neighbouring tile.  w = 0: the tile's first part, 1: its last part.
+      auto split_scale = [&](int w, int hd) {
+        const float m_own = s_al[kAlphaSplitOff + w * 32 + hd * 2], s_own = s_al[kAlphaSplitOff + w * 32 + hd * 2 + 1];
+        const float m_oth = s_nb[w * 32 + hd * 2], s_oth = s_nb[w * 32 + hd * 2 + 1];
+        const float mg = fmaxf(m_own, m_oth);
+        const float f_own = fast_ex2(m_own - mg);
+        return f_own / fmaf(s_own, f_own, s_oth * fast_ex2(m_oth - mg));
+      };
+      // part table (one broadcast 16-byte read per use: keeps the per-part index arithmetic out of the unrolled loops)
+      int4* s_ptab = reinterpret_cast<int4*>(es + P::e_ptab);
+      if (ROLE != ROLE_V && tg < NDMAX) s_ptab[tg] = make_int4(T.first(tg), tg < T.nd ? T.count(tg) : 0, T.aoff(tg), 0);
+      auto part_split = [&](int pd) { return s_ptab[pd].y < T.deg; };   // (deg = 0: never)
       const float* s_vs = reinterpret_cast<const float*>(slot + P::alpha_bytes);   // ROLE_XV: shape part of the VN maps [feat | dir][16][3]
 
-      if (ROLE != ROLE_K) cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
+      if (ROLE != ROLE_K) { if (BOTH) cp_async_wait<1>(); else cp_async_wait<0>(); }   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
       mbar_wait(bar + B_D2_FULL + bb, (t / NB2) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
-      if (ROLE != ROLE_K) named_sync(bar_id, E2_GRP_THREADS);      // staged alpha / shape / rel visible to the group
-      if (SMB_DBG(a, 1)) { fence_before_sync(); mbar_arrive(bar + B_E2_DONE + bb); named_sync(bar_id, E2_GRP_THREADS); continue; }
+      if (ROLE != ROLE_K) named_sync(sync_id, sn);      // staged alpha / shape / rel visible to the group(s)
 
       if (ROLE == ROLE_K) {
         // logits of this row: the 16 accumulator columns of its destination (already scaled by log2(e) / sqrt(dh) through q;
@@ -684,9 +742,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           float* at = a.alpha_t + (size_t)(t_begin + t) * kAlphaTileFloats;
           for (int pair = tg >> 1; pair < T.nd * kHeads; pair += E2_GRP_THREADS / 2) {
             const int pd = pair >> 4, hd = pair & 15;
-            const float* col = s_log + (pd * T.deg + 16 * part) * LS + hd;
-            const float* gw = s_ew + pd * T.deg + 16 * part;
-            const int nq = T.deg - 16 * part;      // valid slots of this half (may be <= 0)
+            const int4 pt = s_ptab[pd];
+            const int first = pt.x, cnt = pt.y;
+            const bool split = cnt < T.deg;        // the destination continues in a neighbouring tile: alpha stays unnormalised
+            const float* col = s_log + (first + 16 * part) * LS + hd;
+            const float* gw = s_ew + first + 16 * part;
+            const int nq = cnt - 16 * part;        // valid slots of this half (may be <= 0)
             float lv[16];
             float mx = -INFINITY;
 #pragma unroll
@@ -699,17 +760,27 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
             for (int qq = 0; qq < 16; ++qq) { lv[qq] = fast_ex2(lv[qq] - mx); se += lv[qq]; }
             se += __shfl_xor_sync(0xffffffffu, se, 1);
-            const float inv = 1.f / se;
+            const float inv = split ? 1.f : 1.f / se;
             float asum = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 16; ++qq) { lv[qq] = qq < nq ? lv[qq] * inv * gw[qq] : 0.f; asum += lv[qq]; }
             asum += __shfl_xor_sync(0xffffffffu, asum, 1);
-            float4* dst = reinterpret_cast<float4*>(at + (hd * T.nd + pd) * SL + 16 * part);
+            float4* dst = reinterpret_cast<float4*>(at + hd * hs + pt.z + 16 * part);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-              if (16 * part + 4 * q4 < SL) dst[q4] = make_float4(lv[4 * q4], lv[4 * q4 + 1], lv[4 * q4 + 2], lv[4 * q4 + 3]);
-            if (part == 0) at[kAlphaSumOff + hd * NDMAX + pd] = asum;
+              if (16 * part + 4 * q4 < cnt) dst[q4] = make_float4(lv[4 * q4], lv[4 * q4 + 1], lv[4 * q4 + 2], lv[4 * q4 + 3]);
+            if (part == 0) {
+              at[kAlphaSumOff + hd * NDMAX + pd] = asum;
+              if (split) {
+                float* sp = at + kAlphaSplitOff + ((pd == 0 && T.head_split()) ? 0 : 32) + hd * 2;
+                sp[0] = mx; sp[1] = se;
+              }
+            }
           }
+          // the rows a split destination's two parts accumulate into (ROLE_V: agg, ROLE_XV: the o sums in the vn row) start at zero;
+          // the tile that holds the FIRST part clears them
+          if (T.tail_split() && a.zero_ptr && tg < a.zero_len)
+            a.zero_ptr[(size_t)(T.a0 + T.d0 + T.nd - 1) * a.zero_stride + a.zero_off + tg] = 0.f;
         }
       } else if (ROLE == ROLE_V) {
         // thread = output channel c (TMEM lane), columns = edge rows
@@ -718,13 +789,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         if (T.deg == 0) {   // single-atom molecule: empty neighbour sum
           a.agg[(size_t)(T.a0 + T.d0) * H + c] = 0.f;
         } else {
-          // a destination's deg <= 31 columns are read as ONE 32-column load (16 when deg <= 16) -- whatever follows them, the
+          // ROLE_V runs on the whole-destination tile list (smb_api.cu): part pd = destination pd, deg rows, no split parts.
+          // A destination's deg <= 31 columns are read as ONE 32-column load (16 when deg <= 16) -- whatever follows them, the
           // next destination's columns or the spare TMEM columns behind the ring, is multiplied by the zero padding of its
           // alpha slots (SL = deg rounded up to 4) or not used at all -- and two destinations share one tcgen05.wait::ld:
           // the load latency is paid nd / 2 times per tile.  Groups of four slots: one 16-byte alpha load, two packed FMAs.
+          const int SL = (T.deg + 3) & ~3;
           const int n4 = SL >> 2;
           auto reduce32 = [&](int pd, const uint32_t (&v)[32]) {
-            const float* al = s_al + (hq * T.nd + pd) * SL;
+            const float* al = s_al + hq * hs + pd * SL;
             uint64_t acc2 = 0ull;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -755,8 +828,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           fence_before_sync();
           mbar_arrive(bar + B_E2_DONE + bb);
           if (valid) {
-            const float* al = s_al + dl * SL + (r - dl * T.deg);     // + head * nd * SL
-            const int hs = T.nd * SL;
+            const int4 pt = s_ptab[dl];
+            const float* al = s_al + pt.z + (r - pt.x);     // + head * hs
 #pragma unroll
             for (int hh = 0; hh < 16; ++hh) s_log[r * LS + hh] = al[hh * hs] * (__uint_as_float(v[hh]) + s_b2[hh]);
           }
@@ -765,13 +838,17 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         // o_i^a = sum_j alpha e_w w (x_i - x_j)
         for (int p = tg; p < T.nd * kHeads; p += E2_GRP_THREADS) {
           const int pd = p >> 4, hd = p & 15;
-          const int r0 = pd * T.deg;
+          const int r0 = s_ptab[pd].x, cnt = s_ptab[pd].y;
           float ox = 0.f, oy = 0.f, oz = 0.f;
 #pragma unroll 4
-          for (int q = 0; q < T.deg; ++q) {
+          for (int q = 0; q < cnt; ++q) {
             const float w = s_log[(r0 + q) * LS + hd];
             const float4 rl = s_rel[r0 + q];
             ox = fmaf(w, rl.x, ox); oy = fmaf(w, rl.y, oy); oz = fmaf(w, rl.z, oz);
+          }
+          if (cnt < T.deg) {   // incomplete part: to the destination's softmax (the other part is in a neighbouring tile)
+            const float sc = split_scale((pd == 0 && T.head_split()) ? 0 : 1, hd);
+            ox *= sc; oy *= sc; oz *= sc;
           }
           float* o = s_o + (pd * kHeads + hd) * 4;
           o[0] = ox; o[1] = oy; o[2] = oz;
@@ -782,6 +859,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
           const int ch = lane & 15, which = lane >> 4;
           const float* w = s_vnw + (which * kHeads + ch) * kVnStride;
           const float* so = s_o + pd * kHeads * 4;
+          if (part_split(pd)) {
+            // a destination split between two tiles: both parts add their o sums into the vn row (cleared by ROLE_K; two
+            // addends: deterministic); its VN maps and BatchNorm terms follow in xv_split_finish_kernel
+            float* acc = a.vn + (size_t)(T.a0 + T.d0 + pd) * kVnRow + 3;
+            if (lane < kHeads) { atomicAdd(acc + lane * 3, so[lane * 4]); atomicAdd(acc + lane * 3 + 1, so[lane * 4 + 1]); atomicAdd(acc + lane * 3 + 2, so[lane * 4 + 2]); }
+            continue;
+          }
           const float* xp = a.x + (size_t)(T.a0 + T.d0 + pd) * 3;
           const float xi = __ldg(xp), yi = __ldg(xp + 1), zi = __ldg(xp + 2);
           float vx = w[0] * xi, vy = w[0] * yi, vz = w[0] * zi;
@@ -809,9 +893,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
       }
       SMB_TRACE(6, t, tg == 0);
-      named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slot are reused by the group's next tile
+      named_sync(sync_id, sn);   // scratch and the staging slot are reused by the group's next tile (ROLE_V: by tile t + 2)
       if (ROLE != ROLE_K) {
-        if (t + NG < nt) stage(t + NG, Tile(td_cur));
+        if (BOTH) { if (t + 2 < nt) stage(t + 2, Tile(td_nx)); }
+        else if (t + NG < nt) stage(t + NG, Tile(td_cur));
         cp_async_commit();
       }
     }   // tiles
@@ -973,22 +1058,46 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 }
 
 // ---- static tile list -------------------------------------------------------------------------------
-__device__ __forceinline__ int tiles_of(int n, int k) {
+// Tiles of a molecule of n atoms (deg = min(k, n - 1) neighbour slots per destination, E = n deg edge slots).
+//   split = false: whole destinations, min(128 / deg, NDMAX) per tile (27 atoms: 4 x 26 = 104 of 128 rows, 7 tiles)
+//   split = true : consecutive runs of the E slots, all about E / ceil(E / 128) rows long, that may begin and end inside a
+//                  destination (27 atoms: 6 x 117 rows), never more than NDMAX parts
+struct TileWalk {
+  int deg, E, target, e;
+  bool split;
+  __device__ __forceinline__ TileWalk(int n, int k, bool split_) : deg(min(k, n - 1)), e(0), split(split_) {
+    E = n * deg;
+    const int per = deg > 0 ? min(TM / deg, NDMAX) * deg : 0;
+    target = split ? (E + (E + TM - 1) / TM - 1) / max((E + TM - 1) / TM, 1) : per;
+  }
+  __device__ __forceinline__ bool done() const { return e >= E; }
+  // next tile: first slot e0, rows, parts
+  __device__ __forceinline__ void next(int& e0, int& rows, int& d0, int& nd) {
+    e0 = e;
+    d0 = e / deg;
+    rows = min(target, E - e);
+    if ((e + rows - 1) / deg - d0 + 1 > NDMAX) rows = (d0 + NDMAX) * deg - e;
+    nd = (e + rows - 1) / deg - d0 + 1;
+    e += rows;
+  }
+};
+__device__ __forceinline__ int tiles_of(int n, int k, bool split) {
   if (n <= 0) return 0;
-  const int deg = min(k, n - 1);
-  if (deg == 0) return 1;
-  const int per = min(TM / deg, NDMAX);
-  return (n + per - 1) / per;
+  if (min(k, n - 1) == 0) return 1;
+  TileWalk w(n, k, split);
+  int cnt = 0, e0, rows, d0, nd;
+  while (!w.done()) { w.next(e0, rows, d0, nd); ++cnt; }
+  return cnt;
 }
 
-__global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict__ mol_ptr, int n_mols, int k, int4* __restrict__ tiles,
+__global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict__ mol_ptr, int n_mols, int k, int split, int4* __restrict__ tiles,
                                                            int* __restrict__ n_tiles) {
   __shared__ int s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per_thread = (n_mols + 1023) / 1024;
   const int m0 = min(n_mols, tid * per_thread), m1 = min(n_mols, m0 + per_thread);
   int cnt = 0;
-  for (int m = m0; m < m1; ++m) cnt += tiles_of(mol_ptr[m + 1] - mol_ptr[m], k);
+  for (int m = m0; m < m1; ++m) cnt += tiles_of(mol_ptr[m + 1] - mol_ptr[m], k, split != 0);
   int inc = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -1013,12 +1122,73 @@ __global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict
     const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
     if (n <= 0) continue;
     const int deg = min(k, n - 1);
-    const int per = deg > 0 ? min(TM / deg, NDMAX) : 1;
-    const int recip = deg > 0 ? 65536 / deg + 1 : 0;
-    for (int d0 = 0; d0 < n; d0 += per) {
-      const int nd = min(per, n - d0);
-      tiles[off++] = make_int4(a0, m, n | (d0 << 8) | (nd << 16) | (deg << 24), recip);
+    if (deg == 0) { tiles[off++] = make_int4(a0, m, n | (1 << 16), 0); continue; }   // single atom: one empty tile
+    const int recip = 65536 / deg + 1;
+    TileWalk w(n, k, split != 0);
+    while (!w.done()) {
+      int e0, rows, d0, nd;
+      w.next(e0, rows, d0, nd);
+      tiles[off++] = make_int4(a0, m | ((e0 - d0 * deg) << 24), n | (d0 << 8) | (nd << 16) | (deg << 24), recip | (rows << 20));
     }
+  }
+}
+
+// ---- destinations split between two tiles (ROLE_XV): VN linear maps + BatchNorm terms once both parts' o sums are in the vn row
+__global__ void __launch_bounds__(256) xv_split_finish_kernel(EdgeArgs a, int row0) {
+  __shared__ float s_w[2 * kHeads * kVnStride];
+  __shared__ float s_o[8][kHeads * 3];
+  __shared__ float s_bn[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int p = tid; p < kHeads * kVnStride; p += 256) { s_w[p] = a.vn_feat[p]; s_w[kHeads * kVnStride + p] = a.vn_dir[p]; }
+  __syncthreads();
+  const int n_tiles = *a.n_tiles;
+  const int ch = lane & 15, which = lane >> 4;
+  float bn_s = 0.f, bn_q = 0.f;
+  for (int t = blockIdx.x * 8 + warp; t < n_tiles; t += gridDim.x * 8) {   // fixed assignment: deterministic partial sums
+    const Tile T(__ldg(a.tiles + t));
+    if (T.deg == 0 || !T.tail_split()) continue;
+    const int atom = T.a0 + T.d0 + T.nd - 1;
+    float* row = a.vn + (size_t)atom * kVnRow;
+    float* so = s_o[warp];
+    so[lane] = row[3 + lane];
+    if (lane < 16) so[32 + lane] = row[35 + lane];
+    __syncwarp();
+    const float* w = s_w + (which * kHeads + ch) * kVnStride;
+    const float* xp = a.x + (size_t)atom * 3;
+    const float xi = __ldg(xp), yi = __ldg(xp + 1), zi = __ldg(xp + 2);
+    float vx = w[0] * xi, vy = w[0] * yi, vz = w[0] * zi;
+#pragma unroll
+    for (int cc = 0; cc < kHeads; ++cc) {
+      const float wc = w[1 + cc];
+      vx = fmaf(wc, so[cc * 3], vx); vy = fmaf(wc, so[cc * 3 + 1], vy); vz = fmaf(wc, so[cc * 3 + 2], vz);
+    }
+    {
+      const float* vs = a.vn_shape + (size_t)T.mol * (2 * kHeads * 3) + (which * kHeads + ch) * 3;
+      vx += __ldg(vs); vy += __ldg(vs + 1); vz += __ldg(vs + 2);
+    }
+    float sm = 0.f;
+    if (lane < 3) {
+#pragma unroll
+      for (int cc = 0; cc < kHeads; ++cc) sm += so[cc * 3 + lane];
+    }
+    __syncwarp();
+    row[3 + which * 48 + ch * 3] = vx; row[4 + which * 48 + ch * 3] = vy; row[5 + which * 48 + ch * 3] = vz;
+    if (lane < 3) row[lane] = sm * (1.f / kHeads);
+    if (which == 0) {
+      const float nu = sqrtf(vx * vx + vy * vy + vz * vz) + 1e-6f;
+      bn_s += nu; bn_q = fmaf(nu, nu, bn_q);
+    }
+    __syncwarp();
+  }
+  // lanes < 16 hold channel sums: row layout [sum | sum of squares] like the edge kernel's partial rows
+  const float qv = __shfl_sync(0xffffffffu, bn_q, lane & 15);
+  s_bn[warp][lane] = lane < 16 ? bn_s : qv;
+  __syncthreads();
+  if (warp == 0) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) acc += s_bn[w8][lane];
+    a.bn_partial[(size_t)(row0 + blockIdx.x) * 32 + lane] = acc;
   }
 }
 
@@ -1056,8 +1226,17 @@ bool edge_ws_supported(const smb_model_dims& d, int n_max) {
   return d.precision == SMB_PREC_BF16 && d.hidden == H && n_max >= 1 && n_max <= G && d.k >= 1;
 }
 
-int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st) {
-  build_tiles_kernel<<<1, 1024, 0, st>>>(mol_ptr, n_mols, k, tiles, n_tiles);
+int launch_build_tiles(const int* mol_ptr, int n_mols, int k, bool split, int4* tiles, int* n_tiles, cudaStream_t st) {
+  static const int allow = getenv("SMB_TILE_SPLIT") ? atoi(getenv("SMB_TILE_SPLIT")) : 1;   // 0: whole destinations everywhere (A/B runs)
+  build_tiles_kernel<<<1, 1024, 0, st>>>(mol_ptr, n_mols, k, split && allow ? 1 : 0, tiles, n_tiles);
+  return (int)cudaGetLastError();
+}
+
+int launch_xv_split_finish(const EdgeArgs& a, int bn_rows_in, int* bn_rows_out, cudaStream_t st) {
+  int grid = device_sm_count();
+  if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
+  xv_split_finish_kernel<<<grid, 256, 0, st>>>(a, bn_rows_in);
+  if (bn_rows_out) *bn_rows_out = bn_rows_in + grid;
   return (int)cudaGetLastError();
 }
 

@@ -159,6 +159,7 @@ Workspace build_workspace(const smb_model_dims& d, int N, int B) {
     }
   }
   w.tiles = c.take(16 + (size_t)w.max_tiles * 16);
+  w.tiles_s = c.take(16 + (size_t)w.max_tiles * 16);
   w.total = c.off;
   return w;
 }

@@ -129,14 +129,20 @@ struct EdgeArgs {
   const void* abh;         // bf16 node projections in per-molecule operand layout (node_mlp_kernel out1_h)
   const int4* tiles;       // static tile list (build_tiles_kernel)
   const int* n_tiles;
-  float* alpha_t;          // [tile][kAlphaTileFloats]: [16 heads][nd][SL] + sums  (ROLE_K out; ROLE_V / ROLE_XV in)
+  float* alpha_t;          // [tile][kAlphaTileFloats] (smb_layout.h)  (ROLE_K out; ROLE_V / ROLE_XV in)
+  // ROLE_K: rows that ROLE_V / ROLE_XV accumulate into from two tiles (a destination split between tiles) are cleared here:
+  // floats [zero_off, zero_off + zero_len) of row `atom` of zero_ptr (row stride zero_stride)
+  float* zero_ptr; int zero_stride, zero_off, zero_len;
   int dbg;                 // SMB_WS_DBG bit mask (timing experiments only: results are wrong when set)
 };
 // bn_rows_out (ROLE_XV): number of [32]-float rows of a.bn_partial the launch writes
 int launch_edge(const smb_model_dims& d, int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 // warp-specialised tcgen05 pipeline (smb_edge_ws.cu): plain-bf16 mode, molecules of <= 32 atoms, all three roles together
 bool edge_ws_supported(const smb_model_dims& d, int n_max);
-int launch_build_tiles(const int* mol_ptr, int n_mols, int k, int4* tiles, int* n_tiles, cudaStream_t st);
+int launch_build_tiles(const int* mol_ptr, int n_mols, int k, bool split, int4* tiles, int* n_tiles, cudaStream_t st);
+// ROLE_XV follow-up: VN maps + BatchNorm partial sums of the destinations whose rows were split between two tiles (their o sums
+// were accumulated into the vn rows); writes *bn_rows_out further rows of a.bn_partial behind the bn_rows_in rows of the edge launch
+int launch_xv_split_finish(const EdgeArgs& a, int bn_rows_in, int* bn_rows_out, cudaStream_t st);
 int launch_edge_ws(int role, const EdgeArgs& a, int* bn_rows_out, cudaStream_t st);
 int debug_ws_trace(long long* host_out);   // -DSMB_DEBUG builds: [15 events][128 tiles] clock64 stamps of CTA 0 (SMB_WS_DBG & 16)
 

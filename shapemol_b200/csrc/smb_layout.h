@@ -66,11 +66,18 @@ struct NodeMlpOff {
 // q of the tcgen05 node kernel: bf16, pre-multiplied by log2(e) / sqrt(head_dim), as a chunk image -- one 16-byte chunk per
 // (row, head):  byte offset of (row r, head h) = (r / 128) * 32768 + h * 2048 + (r % 128) * 16   (8 channels of the head)
 constexpr int kQChunkBlockBytes = 128 * 128 * 2;
-// alpha (softmax x gate) of the warp-specialised edge pipeline, per tile: [16 heads][nd destinations][SL slots] fp32 with
-// SL = deg rounded up to 4 (slots >= deg are zero), then sum_j alpha per (head, destination) at float kAlphaSumOff + h * 8 + d.
-// nd * SL <= 144 for nd <= 8, nd * deg <= 128.
-constexpr int kAlphaSumOff = 16 * 144;
-constexpr int kAlphaTileFloats = kAlphaSumOff + 16 * 8;   // 2432 floats = 9728 bytes per tile
+// alpha (softmax x gate) of the warp-specialised edge pipeline, per tile of <= 128 consecutive edge rows of one molecule:
+//   [16 heads][parts] fp32, part pd = the tile's rows of its pd-th destination (cnt(pd) rows: a tile may begin and end inside a
+//   destination), rup4(cnt) slots each (slots >= cnt are zero); head stride = sum of the part lengths (<= 128 + 3 * 8) rounded up
+//   to 4 mod 16 floats, so that the four heads a warp of ROLE_V reads at once fall into different shared-memory banks.
+//   float kAlphaSumOff   + h * 8 + pd        sum_j alpha of the part
+//   float kAlphaSplitOff + w * 32 + h * 2    (max logit, sum of exponentials) of the tile's first (w = 0) / last (w = 1) part when
+//                                            that destination continues in the neighbouring tile: such parts hold
+//                                            exp2(logit - max) x gate, NOT normalised, and the consumers combine the two parts
+constexpr int kAlphaHeadMax = 164;
+constexpr int kAlphaSumOff = 16 * kAlphaHeadMax;
+constexpr int kAlphaSplitOff = kAlphaSumOff + 16 * 8;
+constexpr int kAlphaTileFloats = kAlphaSplitOff + 64;   // 2816 floats = 11264 bytes per tile (a 27-atom tile uses 2304)
 constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
 constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
 constexpr int kNodeOutKx = 272;                         // node_output: 128 (agg) + 128 (h) + 16 (bias hi | bias lo | zeros)
@@ -133,7 +140,8 @@ struct Workspace {
   size_t g_idx;            // int32 [3][M]: destination / source atom, molecule (-1: empty slot)
   size_t g_node, g_bn;     // [N][H], [N][32]
   size_t g_wimg, g_wimg_bytes;   // pre-split weight image of the GEMM in flight (smb_tc_gemm.cu)
-  size_t tiles;     // [max_tiles] int4 tile descriptors, preceded by the tile count (16 bytes)
+  size_t tiles;     // [max_tiles] int4 tile descriptors, preceded by the tile count (16 bytes): whole destinations per tile (X2H block)
+  size_t tiles_s;   // same, tiles that may begin / end inside a destination (gate, H2X block)
   int max_tiles;    // N/4 + B + 8: a tile holds >= 4 destination atoms unless it is the last of its molecule
   int bn_part_rows;
 };
