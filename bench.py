@@ -389,7 +389,8 @@ def main():
         kt = prof_kernels(eng, sampler, ['edge_k', 'edge_v', 'node_pre', 'node_out'])
         k_ms = kt['edge_k'][0]
         x2h_ms = kt['node_pre'][0] + kt['edge_k'][0] + kt['edge_v'][0] + kt['node_out'][0]
-        n_tiles, rows = tiles_and_rows(sizes, args.k)
+        n_tiles, rows = tiles_and_rows(sizes, args.k, split=False)   # X2H block: whole destinations per tile
+        n_tiles_s, _ = tiles_and_rows(sizes, args.k)                 # gate + H2X block: tiles may split a destination
         f_ref_k, f_min_k = E * (F_REF_EDGE_MLP + 2 * H), E * (F_MIN_EDGE_MLP + 2 * H)
         f_ref_blk, f_min_blk = E * F_REF_X2H_EDGE + N * F_REF_X2H_NODE, E * F_MIN_X2H_EDGE + N * F_MIN_X2H_NODE
         f_ref_step, f_min_step = E * F_REF_STEP_EDGE + N * F_REF_STEP_NODE, E * F_MIN_STEP_EDGE + N * F_MIN_STEP_NODE
@@ -414,7 +415,8 @@ def main():
                      'F_ref_per_molecule_gflop': f_ref_step / max(B, 1) / 1e9, 'F_min_per_molecule_gflop': f_min_step / max(B, 1) / 1e9},
             'hbm_bytes_per_launch_algorithmic': bytes_alg, 'hbm_gbs': bytes_alg / (k_ms * 1e-3) / 1e9,
             'hbm_frac': bytes_alg / (k_ms * 1e-3) / 1e9 / hbm,
-            'tile_rows_used': rows / (128.0 * max(n_tiles, 1)), 'tiles': n_tiles,
+            'tile_rows_used': {'x2h_block': rows / (128.0 * max(n_tiles, 1)), 'gate_h2x_block': rows / (128.0 * max(n_tiles_s, 1))},
+            'tiles': {'x2h_block': n_tiles, 'gate_h2x_block': n_tiles_s},
         }
 
     secondary = rank == 0 and world == 1 and not args.quick
@@ -427,11 +429,12 @@ def main():
         smp1 = Sampler(eng, p1.to(dev), v1.to(dev), b1.to(dev), sh1.to(dev), num_steps=1000, noise='philox', seed=2021,
                        keep_traj=False, use_graph=True, n_mols=B1)
         ms1 = timed_graph_steps(smp1, args.steps, args.warmup, barrier)
-        t1, r1 = tiles_and_rows(s1, args.k)
+        t1, r1 = tiles_and_rows(s1, args.k, split=False)
+        t1s, _ = tiles_and_rows(s1, args.k)
         kt1 = prof_kernels(eng, smp1, ['edge_k'])
         line_extra['configs1'] = {'workload': '100 shapes x 50 molecules, MOSES size prior (9..27 atoms, mean 21.4), k=%d' % args.k,
                                   'molecules': B1, 'atoms': N1, 'ms_per_step': ms1, 'mol_steps_per_s': B1 / (ms1 * 1e-3),
-                                  'molecules_per_s_1000_steps': B1 / (ms1 * 1e-3) / 1000.0, 'tile_rows_used': r1 / (128.0 * t1),
+                                  'molecules_per_s_1000_steps': B1 / (ms1 * 1e-3) / 1000.0, 'tile_rows_used': {'x2h_block': r1 / (128.0 * t1), 'gate_h2x_block': r1 / (128.0 * t1s)},
                                   'edge_k_ms_per_launch': kt1['edge_k'][0]}
         del smp1
 

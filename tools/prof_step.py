@@ -29,16 +29,18 @@ def main():
     smp = Sampler(model._engine(), pos.to(dev), v.to(dev), batch.to(dev), shape.to(dev), num_steps=1000, noise='philox', seed=2021,
                   keep_traj=False, use_graph=True, n_mols=B)
     ms = bench.timed_graph_steps(smp, args.steps, 3, torch.cuda.synchronize)
-    tiles, rows = bench.tiles_and_rows(sizes, args.k)
-    print('workload %d mols x %s  atoms %d  edges %d  tiles %d  rows used %.3f' % (
-        B, args.fixed_atoms or 'prior', int(sizes.sum()), rows, tiles, rows / (128.0 * tiles)))
+    tiles, rows = bench.tiles_and_rows(sizes, args.k, split=False)
+    tiles_s, _ = bench.tiles_and_rows(sizes, args.k)
+    print('workload %d mols x %s  atoms %d  edges %d  tiles %d (X2H) / %d (gate, H2X)  rows used %.3f / %.3f' % (
+        B, args.fixed_atoms or 'prior', int(sizes.sum()), rows, tiles, tiles_s, rows / (128.0 * tiles), rows / (128.0 * tiles_s)))
     print('step %.3f ms  %.0f mol-steps/s' % (ms, B / (ms * 1e-3)))
     if args.precision == 'bf16':
         kt = bench.prof_kernels(model._engine(), smp, ['edge_k', 'edge_v', 'edge_xv', 'node_pre', 'node_out', 'gate', 'knn', 'head'])
         tot = 0.0
         for c, (t, n) in kt.items():
             tot += t * n
-            print('  %-9s %8.4f ms x %2d = %7.3f ms (%4.1f%%)  %.1f ns/tile' % (c, t, n, t * n, 100 * t * n / ms, t * 1e6 / tiles * 148))
+            nt = {'edge_xv': tiles_s, 'gate': tiles_s, 'edge_k': 0.5 * (tiles + tiles_s)}.get(c, tiles)   # edge_k: mean of the two blocks
+            print('  %-9s %8.4f ms x %2d = %7.3f ms (%4.1f%%)  %.1f ns/tile' % (c, t, n, t * n, 100 * t * n / ms, t * 1e6 / nt * 148))
         print('  other      %7.3f ms' % (ms - tot))
 
 
