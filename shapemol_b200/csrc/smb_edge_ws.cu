@@ -220,10 +220,7 @@ struct Tile {
   __device__ __forceinline__ bool tail_split() const { return s0 + nrows < nd * deg; }
   // alpha block: part pd starts at float aoff(pd) of a head's hstride() floats (smb_layout.h)
   __device__ __forceinline__ int aoff(int pd) const { return pd == 0 ? 0 : ((count(0) + 3) & ~3) + (pd - 1) * ((deg + 3) & ~3); }
-  __device__ __forceinline__ int hstride() const {
-    const int h = aoff(nd - 1) + ((count(nd - 1) + 3) & ~3);
-    return h + ((4 - h) & 15);   // 4 mod 16: conflict-free 16-byte reads of four heads (ROLE_V)
-  }
+  __device__ __forceinline__ int hstride() const { return aoff(nd - 1) + ((count(nd - 1) + 3) & ~3); }
 };
 
 // timing experiments (SMB_WS_DBG & 16): per-tile clock64 stamps of CTA 0's roles, read back with smb_debug_ws_trace
@@ -624,8 +621,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         const float* src = a.alpha_t + (size_t)(t_begin + t) * kAlphaTileFloats;
         float* dst = reinterpret_cast<float*>(slot);
 #pragma unroll
-        for (int p = sid; p < 4 * T.hstride(); p += sn) cp_async16(dst + p * 4, src + p * 4);   // 16 heads x hstride floats
-        if (sid < (kAlphaTileFloats - kAlphaSumOff) / 4) cp_async16(dst + kAlphaSumOff + sid * 4, src + kAlphaSumOff + sid * 4);   // sums | split statistics
+        if (ROLE == ROLE_V) {   // whole-destination tiles: nd x SL floats per head; fixed trip count (the block's unused tail included)
+#pragma unroll
+          for (int p = tg; p < kAlphaTileFloats / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
+        } else {
+          for (int p = sid; p < 4 * T.hstride(); p += sn) cp_async16(dst + p * 4, src + p * 4);   // 16 heads x hstride floats
+          if (sid < (kAlphaTileFloats - kAlphaSumOff) / 4) cp_async16(dst + kAlphaSumOff + sid * 4, src + kAlphaSumOff + sid * 4);   // sums | split statistics
+        }
         // statistics of the other part of a split destination: the previous tile's last part | the next tile's first part
         // (read only when this tile's first / last part is incomplete, which implies that the neighbour exists)
         if (ROLE != ROLE_V && sid >= sn - 16) {
@@ -667,8 +669,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       if (ROLE != ROLE_K && !BOTH && t + NG < nt && tg < (kAlphaTileFloats * 4 + 127) / 128) {
         // the staging slot is busy until this tile is done: pull the group's next alpha block into L2 meanwhile, so that
         // the cp.async issued after the trailing barrier does not pay the DRAM latency
+        // (only the lines that tile uses: 16 heads x hstride floats, then the sums | split statistics behind kAlphaSumOff)
         const float* nxt = a.alpha_t + (size_t)(t_begin + t + NG) * kAlphaTileFloats + tg * 32;
-        if (!SMB_DBG(a, 32)) asm volatile("prefetch.L2 [%0];" :: "l"(nxt));
+        if (ROLE == ROLE_V || tg * 32 < 16 * Tile(td_cur).hstride() || tg * 32 + 31 >= kAlphaSumOff) asm volatile("prefetch.L2 [%0];" :: "l"(nxt));
         // ... and the split statistics of that tile's neighbours (the 128-byte line of the previous tile's last part / the next
         // tile's first part), when it begins / ends inside a destination
         if (ROLE != ROLE_V && tg < 2) {
@@ -1233,8 +1236,10 @@ int launch_build_tiles(const int* mol_ptr, int n_mols, int k, bool split, int4* 
 }
 
 int launch_xv_split_finish(const EdgeArgs& a, int bn_rows_in, int* bn_rows_out, cudaStream_t st) {
-  int grid = device_sm_count();
-  if (grid > kEdgeMaxCtas) grid = kEdgeMaxCtas;
+  // one warp per tile with a dependent load chain (descriptor -> vn row -> stores): many small CTAs hide its latency.  Every CTA
+  // writes one BatchNorm partial row (fixed tile assignment: deterministic), the workspace holds kEdgeMaxCtas * kEdgeWarps rows.
+  int grid = device_sm_count() * 8;
+  if (grid > kEdgeMaxCtas * (kEdgeWarps - 1)) grid = kEdgeMaxCtas * (kEdgeWarps - 1);
   xv_split_finish_kernel<<<grid, 256, 0, st>>>(a, bn_rows_in);
   if (bn_rows_out) *bn_rows_out = bn_rows_in + grid;
   return (int)cudaGetLastError();

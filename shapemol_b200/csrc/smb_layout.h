@@ -68,16 +68,15 @@ struct NodeMlpOff {
 constexpr int kQChunkBlockBytes = 128 * 128 * 2;
 // alpha (softmax x gate) of the warp-specialised edge pipeline, per tile of <= 128 consecutive edge rows of one molecule:
 //   [16 heads][parts] fp32, part pd = the tile's rows of its pd-th destination (cnt(pd) rows: a tile may begin and end inside a
-//   destination), rup4(cnt) slots each (slots >= cnt are zero); head stride = sum of the part lengths (<= 128 + 3 * 8) rounded up
-//   to 4 mod 16 floats, so that the four heads a warp of ROLE_V reads at once fall into different shared-memory banks.
+//   destination), rup4(cnt) slots each (slots >= cnt are zero); head stride = sum of the part lengths <= 128 + 3 * 8.
 //   float kAlphaSumOff   + h * 8 + pd        sum_j alpha of the part
 //   float kAlphaSplitOff + w * 32 + h * 2    (max logit, sum of exponentials) of the tile's first (w = 0) / last (w = 1) part when
 //                                            that destination continues in the neighbouring tile: such parts hold
 //                                            exp2(logit - max) x gate, NOT normalised, and the consumers combine the two parts
-constexpr int kAlphaHeadMax = 164;
+constexpr int kAlphaHeadMax = 152;
 constexpr int kAlphaSumOff = 16 * kAlphaHeadMax;
 constexpr int kAlphaSplitOff = kAlphaSumOff + 16 * 8;
-constexpr int kAlphaTileFloats = kAlphaSplitOff + 64;   // 2816 floats = 11264 bytes per tile (a 27-atom tile uses 2304)
+constexpr int kAlphaTileFloats = kAlphaSplitOff + 64;   // 2624 floats = 10496 bytes per tile (a 27-atom tile uses 2240)
 constexpr int kNodeKx = 176;                            // 128 (h) + 32 (inv) + 16 (bias hi | bias lo | zeros)
 constexpr int kNodeChunkBytes = 128 * kNodeKx * 2;      // 45056
 constexpr int kNodeOutKx = 272;                         // node_output: 128 (agg) + 128 (h) + 16 (bias hi | bias lo | zeros)
