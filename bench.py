@@ -44,8 +44,8 @@ F_REF_STEP_EDGE = LAYERS * 2 * (4 * K_IN * H + 3 * H * H + H * HEADS) + 2 * (RBF
 F_REF_STEP_NODE = LAYERS * (14 * H * H + 12 * (HEADS + 32 + 1) * HEADS) + 2 * (15 + 8) * H + 2 * (H * H + H * 15)
 F_MIN_STEP_EDGE = LAYERS * (8 * RBF * H + 2 * (3 * H * H + H * HEADS)) + 2 * (RBF * H + H)
 F_MIN_STEP_NODE = LAYERS * (30 * H * H + 12 * (HEADS + 32 + 1) * HEADS) + 2 * (15 + 8) * H + 2 * (H * H + H * 15)
-KERNELS_PER_STEP = 4 + 8 * 9 + 1 + 1 + 1                   # prep, embed, knn, gate | 8 x (3 node, 4 edge, bn, apply) | head | posterior | t--
-#                                                            (the tile list is built once: steps after the first reuse it)
+KERNELS_PER_STEP = 4 + 8 * 10 + 1 + 1 + 1                  # prep, embed, knn, gate | 8 x (3 node, 4 edge, split finish, bn, apply) | head | posterior | t--
+#                                                            (the tile lists are built once: steps after the first reuse them)
 
 
 def ref_like_config(k=32):

@@ -7,4 +7,4 @@ $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'edge_ws_kernel|node_tc5_kernel' -s 12 -c 7 -o gpurun_out/r2_prof_edge $CMD > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
+tail -2 gpurun_out/ncu_list.log; tail -2 gpurun_out/ncu_full.log
