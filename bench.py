@@ -83,12 +83,10 @@ def make_workload(n_shapes, per_shape, seed, fixed_atoms=0):
     return sizes, batch, pos, v, shape
 
 
-def tiles_and_rows(sizes, k, split=None):
+def tiles_and_rows(sizes, k, split=True):
     """Static tile list of the edge pipeline (csrc/smb_edge_ws.cu TileWalk): <= 128 consecutive edge slots of one molecule, at
-    most 8 destinations touched; split (default, SMB_TILE_SPLIT != 0): runs of about E / ceil(E / 128) slots that may begin and
-    end inside a destination, else whole destinations.  Returns (tiles, edge rows)."""
-    if split is None:
-        split = os.environ.get('SMB_TILE_SPLIT', '1') != '0'
+    most 8 destinations touched; split (gate, H2X block): runs of about E / ceil(E / 128) slots that may begin and end inside a
+    destination; else (X2H block) whole destinations.  Returns (tiles, edge rows)."""
     cache, tiles, rows = {}, 0, 0
     for n in sizes.tolist():
         if n not in cache:

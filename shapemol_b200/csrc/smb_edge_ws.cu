@@ -5,9 +5,10 @@
 // to each other through mbarriers so that global-load latency, the two MMAs and the SIMT epilogues of
 // different tiles overlap.
 //
-// Tile = 128 edge rows = `nd` whole destination atoms of ONE molecule, `deg` rows each (the kNN
-// degree min(k, n-1) is the same for every atom of a molecule), built once per forward by
-// build_tiles_kernel.
+// Tile = up to 128 consecutive edge slots of ONE molecule (slot = destination * deg + neighbour; the kNN degree
+// deg = min(k, n-1) is the same for every atom of a molecule) touching nd <= 8 destinations.  Two static lists, built once
+// per batch by build_tiles_kernel: whole destinations per tile (X2H block: ROLE_K + ROLE_V), and equal runs that may begin
+// and end inside a destination (gate, H2X block: ROLE_K + ROLE_XV) -- see struct Tile / TileWalk.
 //
 //   warps 0-1   P     : two rows per thread.  neighbour index, |x_i - x_j|, 20 RBFs, one-hot(i), one-hot(j)
 //                       -> A1[128 x 96] bf16 in a 2-slot smem ring
@@ -602,16 +603,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 
     // what tile `t` needs from global memory, fetched after the group's previous tile: the tile's alpha block / shape
     // (cp.async) and this thread's gate value / relative position (registers)
-    // BOTH (off): both groups of ROLE_V work on every tile (a tile's parts are read in rounds of two; round rd belongs to group
-    // rd & 1; the two staging slots form a ring over the tiles, filled two tiles ahead by all 256 threads).  It halves the
-    // accumulator's hold time but the groups' throughput drops from 1.5 to 2 rounds per five-part tile: measured slower.
-    constexpr bool BOTH = false;
-    const int t_step = BOTH ? 1 : NG;
-    const int sid = BOTH ? e2w * 32 + lane : tg, sn = BOTH ? 2 * E2_GRP_THREADS : E2_GRP_THREADS;   // staging thread index / count
-    const int sync_id = BOTH ? BAR_E2 : bar_id;
     float pre_ew = 0.f, pre_x = 0.f, pre_y = 0.f, pre_z = 0.f;
     auto stage = [&](int t, const Tile& T) {
-      unsigned char* slot = BOTH ? smem + P::o_e2 + (t & 1) * P::e2_bytes + P::e_stage : es + P::e_stage;
+      unsigned char* slot = es + P::e_stage;
       const bool valid = r < T.rows();
       const int dl = valid ? T.dst_of(r) : 0, sl = T.slot_of(r, dl);
       if (ROLE == ROLE_K) {
@@ -625,13 +619,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
 #pragma unroll
           for (int p = tg; p < kAlphaTileFloats / 4; p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);
         } else {
-          for (int p = sid; p < 4 * T.hstride(); p += sn) cp_async16(dst + p * 4, src + p * 4);   // 16 heads x hstride floats
-          if (sid < (kAlphaTileFloats - kAlphaSumOff) / 4) cp_async16(dst + kAlphaSumOff + sid * 4, src + kAlphaSumOff + sid * 4);   // sums | split statistics
+          for (int p = tg; p < 4 * T.hstride(); p += E2_GRP_THREADS) cp_async16(dst + p * 4, src + p * 4);   // 16 heads x hstride floats
+          if (tg < (kAlphaTileFloats - kAlphaSumOff) / 4) cp_async16(dst + kAlphaSumOff + tg * 4, src + kAlphaSumOff + tg * 4);   // sums | split statistics
         }
         // statistics of the other part of a split destination: the previous tile's last part | the next tile's first part
         // (read only when this tile's first / last part is incomplete, which implies that the neighbour exists)
-        if (ROLE != ROLE_V && sid >= sn - 16) {
-          const int q = sid - (sn - 16), w = q >> 3;
+        if (ROLE != ROLE_V && tg >= E2_GRP_THREADS - 16) {
+          const int q = tg - (E2_GRP_THREADS - 16), w = q >> 3;
           if (w ? T.tail_split() : T.head_split())
             cp_async16(slot + P::o_nbst + q * 16, a.alpha_t + (size_t)(t_begin + t + (w ? 1 : -1)) * kAlphaTileFloats + kAlphaSplitOff + (w ? 0 : 32) + (q & 7) * 4);
         }
@@ -650,23 +644,18 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
     };
 
     const int4 zero4 = make_int4(0, 0, 0, 0);
-    const int t_first = BOTH ? 0 : g;
-    int4 td_cur = t_first < nt ? __ldg(tiles + t_first) : zero4;
-    int4 td_nx = t_first + t_step < nt ? __ldg(tiles + t_first + t_step) : zero4;
-    if (t_first < nt) stage(t_first, Tile(td_cur));
+    int4 td_cur = g < nt ? __ldg(tiles + g) : zero4;
+    int4 td_nx = g + NG < nt ? __ldg(tiles + g + NG) : zero4;
+    if (g < nt) stage(g, Tile(td_cur));
     cp_async_commit();
-    if (BOTH) {
-      if (1 < nt) stage(1, Tile(td_nx));
-      cp_async_commit();
-    }
 #pragma unroll 1
-    for (int t = t_first; t < nt; t += t_step) {
+    for (int t = g; t < nt; t += NG) {
       const Tile T(td_cur);
       const float ew_r = pre_ew, relx = pre_x, rely = pre_y, relz = pre_z;
       td_cur = td_nx;
-      if (t + 2 * t_step < nt) td_nx = __ldg(tiles + t + 2 * t_step);
+      if (t + 2 * NG < nt) td_nx = __ldg(tiles + t + 2 * NG);
       if (ROLE == ROLE_K && t + NG < nt) stage(t + NG, Tile(td_cur));   // registers only: the next tile's gate value
-      if (ROLE != ROLE_K && !BOTH && t + NG < nt && tg < (kAlphaTileFloats * 4 + 127) / 128) {
+      if (ROLE != ROLE_K && t + NG < nt && tg < (kAlphaTileFloats * 4 + 127) / 128) {
         // the staging slot is busy until this tile is done: pull the group's next alpha block into L2 meanwhile, so that
         // the cp.async issued after the trailing barrier does not pay the DRAM latency
         // (only the lines that tile uses: 16 heads x hstride floats, then the sums | split statistics behind kAlphaSumOff)
@@ -686,7 +675,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       const bool valid = r < rows;
       const int dl = valid ? T.dst_of(r) : 0;
       const int hs = T.hstride();             // alpha floats per head
-      const unsigned char* slot = BOTH ? smem + P::o_e2 + (t & 1) * P::e2_bytes + P::e_stage : es + P::e_stage;
+      const unsigned char* slot = es + P::e_stage;
       const float* s_al = reinterpret_cast<const float*>(slot);           // ROLE_V / ROLE_XV: the tile's alpha block
       const float* s_nb = reinterpret_cast<const float*>(slot + P::o_nbst);   // neighbours' split statistics [prev last | next first][16][2]
       // factor that turns the unnormalised alpha of an incomplete part into the destination's softmax: this part's (max, sum)
@@ -704,12 +693,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
       auto part_split = [&](int pd) { return s_ptab[pd].y < T.deg; };   // (deg = 0: never)
       const float* s_vs = reinterpret_cast<const float*>(slot + P::alpha_bytes);   // ROLE_XV: shape part of the VN maps [feat | dir][16][3]
 
-      if (ROLE != ROLE_K) { if (BOTH) cp_async_wait<1>(); else cp_async_wait<0>(); }   // this thread's share of tile t's staged data has landed
+      if (ROLE != ROLE_K) cp_async_wait<0>();   // this thread's share of tile t's staged data has landed
       if (ROLE == ROLE_XV) s_rel[r] = make_float4(relx, rely, relz, 0.f);
       mbar_wait(bar + B_D2_FULL + bb, (t / NB2) & 1);
       fence_after_sync();
       SMB_TRACE(5, t, tg == 0);
-      if (ROLE != ROLE_K) named_sync(sync_id, sn);      // staged alpha / shape / rel visible to the group(s)
+      if (ROLE != ROLE_K) named_sync(bar_id, E2_GRP_THREADS);      // staged alpha / shape / rel visible to the group
 
       if (ROLE == ROLE_K) {
         // logits of this row: the 16 accumulator columns of its destination (already scaled by log2(e) / sqrt(dh) through q;
@@ -896,10 +885,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_ws_kernel(EdgeArgs a) {
         }
       }
       SMB_TRACE(6, t, tg == 0);
-      named_sync(sync_id, sn);   // scratch and the staging slot are reused by the group's next tile (ROLE_V: by tile t + 2)
+      named_sync(bar_id, E2_GRP_THREADS);   // scratch and the staging slot are reused by the group's next tile
       if (ROLE != ROLE_K) {
-        if (BOTH) { if (t + 2 < nt) stage(t + 2, Tile(td_nx)); }
-        else if (t + NG < nt) stage(t + NG, Tile(td_cur));
+        if (t + NG < nt) stage(t + NG, Tile(td_cur));
         cp_async_commit();
       }
     }   // tiles
@@ -1230,7 +1218,11 @@ bool edge_ws_supported(const smb_model_dims& d, int n_max) {
 }
 
 int launch_build_tiles(const int* mol_ptr, int n_mols, int k, bool split, int4* tiles, int* n_tiles, cudaStream_t st) {
+#ifdef SMB_DEBUG
   static const int allow = getenv("SMB_TILE_SPLIT") ? atoi(getenv("SMB_TILE_SPLIT")) : 1;   // 0: whole destinations everywhere (A/B runs)
+#else
+  const int allow = 1;
+#endif
   build_tiles_kernel<<<1, 1024, 0, st>>>(mol_ptr, n_mols, k, split && allow ? 1 : 0, tiles, n_tiles);
   return (int)cudaGetLastError();
 }
