@@ -10,19 +10,21 @@
 // per batch by build_tiles_kernel: whole destinations per tile (X2H block: ROLE_K + ROLE_V), and equal runs that may begin
 // and end inside a destination (gate, H2X block: ROLE_K + ROLE_XV) -- see struct Tile / TileWalk.
 //
-//   warps 0-1   P     : two rows per thread.  neighbour index, |x_i - x_j|, 20 RBFs, one-hot(i), one-hot(j)
-//                       -> A1[128 x 96] bf16 in a 2-slot smem ring
-//   warp  18/19 MMA   : (18: loader + GEMM1, 19: GEMM2) cp.async of the molecule's bf16 projection tiles (3-slot ring), then
-//                       GEMM1 (SS)  D[128 x 128] = A1 . [W1r ; A-tile ; B-tile]         (K = 96)
-//                       GEMM2       ROLE_K/XV (TS): D = z . W2^T, z from TMEM;  ROLE_V (SS): D^T = W2 . z^T
-//   warps 4-11  LN : D -> LayerNorm -> ReLU -> z (bf16; TMEM columns, or smem for ROLE_V); thread = (row, column half)
-//   warps 12-27 E2 groups (tiles round-robin):
-//                      ROLE_K  the attention logits come straight out of GEMM2: the query is folded into the second Linear
-//                              per tile,  logit[e, (d, h)] = z_e . M[:, (d, h)],  M = W2^T blockdiag_h(Q_d)  (built by a small
-//                              extra MMA, converted to a bf16 operand by the conversion group), so a row reads the 16 columns
-//                              of its destination; softmax over the destination's rows, x gate -> alpha
+// Roles (warp ids per role: struct Ring; 28 warps, register budgets re-balanced per role with setmaxnreg):
+//   P       4 warps (ROLE_XV: 2, two rows per thread): neighbour index, |x_i - x_j|, 20 RBFs, one-hot(i), one-hot(j)
+//           -> A1[128 x 96] bf16 in a 2-slot smem ring
+//   loader  1 warp (ROLE_XV: inside the GEMM1 warp): bulk copies of the molecule's bf16 projection tiles (3-slot ring)
+//   GEMM1   1 warp: (SS)  D[128 x 128] = A1 . [W1r ; A-tile ; B-tile]         (K = 96)
+//   LN      8 warps: D -> LayerNorm -> ReLU -> z (bf16; TMEM columns, or smem for ROLE_V); thread = (row, column half)
+//   fold    ROLE_K: 1 issuer warp + the 4-warp conversion group: M = W2^T blockdiag_h(Q_d) per tile (a small extra MMA, then
+//           fp32 accumulator -> bf16 operand), so that  logit[e, (d, h)] = z_e . M[:, (d, h)]  comes straight out of GEMM2
+//   GEMM2   1 warp: ROLE_K (TS): D = z . M;  ROLE_XV (TS): D = z . W2^T;  ROLE_V (SS): D^T = W2 . z^T
+//   E2      groups of 4 warps, tiles round-robin (ROLE_K / ROLE_V: 2 groups, ROLE_XV: 4):
+//                      ROLE_K  a row reads the 16 logit columns of its destination; softmax over the destination's rows in the
+//                              tile, x gate -> alpha (+ the part's max / sum when the destination continues in the next tile)
 //                      ROLE_V  sum_j alpha (W2 z + b2), lane = channel, in-thread over the rows
-//                      ROLE_XV alpha w (x_i - x_j) -> VN linear maps -> BatchNorm partial sums
+//                      ROLE_XV alpha w (x_i - x_j) -> VN linear maps -> BatchNorm partial sums (split destinations: o sums added
+//                              into the vn row, finished by xv_split_finish_kernel)
 //
 // TMEM (512 columns): ROLE_K D[2] at 0/128 (GEMM2 overwrites GEMM1's accumulator in place), z[2] at 256/320, the query
 // fold's accumulator at 384.  alpha travels between the kernels tile-strided (smb_layout.h kAlphaTileFloats).
