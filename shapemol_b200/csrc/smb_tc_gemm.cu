@@ -178,17 +178,22 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
 
   float4 ra[NA], rw[NW];                // this thread's pieces of the staged chunk (fp32)
   const bool img = g.use_img != 0;      // W arrives pre-split through bulk copies
+  int arow[NA], arow_seg = -1;          // gathered row of each of this thread's pieces in the current segment (-1: none)
   auto fetch = [&](int c) {             // chunk c -> (segment, k0)
     int s, k0;
     chunk_of(g, c, KC, s, k0);
     const TcGemmSeg& sg = g.seg[s];
+    if (s != arow_seg) {                // the row indices change with the segment only: one dependent load per segment, not per chunk
+      arow_seg = s;
 #pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      const int m = m0 + sr + RSTEP * i;
-      long long arow = -1;
-      if (m < g.M) arow = sg.idx ? (long long)__ldg(sg.idx + bz * g.idx_batch + m) : (long long)m;
-      ra[i] = arow >= 0 ? load4(sg.a + bz * g.a_batch + arow * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < NA; ++i) {
+        const int m = m0 + sr + RSTEP * i;
+        arow[i] = m < g.M ? (sg.idx ? __ldg(sg.idx + bz * g.idx_batch + m) : m) : -1;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+      ra[i] = arow[i] >= 0 ? load4(sg.a + bz * g.a_batch + (long long)arow[i] * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (img) return;
     const float* wb = g.W + bz * g.w_batch + sg.w_off;
 #pragma unroll
@@ -244,11 +249,18 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
         for (int q = 0; q < 4; ++q) {
           const int n = cb + 4 * q;
           float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            o[e] = __uint_as_float(v[4 * q + e]);
-            if (g.bias && n0 + n + e < g.N) o[e] += __ldg(g.bias + n0 + n + e);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias) {
+            if (g.vec_c && n0 + n + 3 < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + n));   // (vec_c: bias is 16-byte aligned too)
+            else {
+              if (n0 + n < g.N) b4.x = __ldg(g.bias + n0 + n);
+              if (n0 + n + 1 < g.N) b4.y = __ldg(g.bias + n0 + n + 1);
+              if (n0 + n + 2 < g.N) b4.z = __ldg(g.bias + n0 + n + 2);
+              if (n0 + n + 3 < g.N) b4.w = __ldg(g.bias + n0 + n + 3);
+            }
           }
+          o[0] = __uint_as_float(v[4 * q]) + b4.x; o[1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+          o[2] = __uint_as_float(v[4 * q + 2]) + b4.z; o[3] = __uint_as_float(v[4 * q + 3]) + b4.w;
           if (g.vec_c && n0 + n + 3 < g.N) {
             float4* dst = reinterpret_cast<float4*>(crow + n);
             if (g.accumulate) { const float4 p = *dst; o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w; }
@@ -287,7 +299,7 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
   for (int s = 0; s < g.n_segs; ++s)
     vec = vec && aligned16(g.seg[s].a) && g.seg[s].lda % 4 == 0 && g.seg[s].w_off % 4 == 0 && g.a_batch % 4 == 0;
   g.vec = vec ? 1 : 0;
-  g.vec_c = (aligned16(g.C) && g.ldc % 4 == 0 && g.c_batch % 4 == 0) ? 1 : 0;
+  g.vec_c = (aligned16(g.C) && g.ldc % 4 == 0 && g.c_batch % 4 == 0 && (!g.bias || aligned16(g.bias))) ? 1 : 0;
   const dim3 grid((unsigned)((g.M + TM - 1) / TM), (unsigned)((g.N + NT_MAX - 1) / NT_MAX), (unsigned)n_batch);
   {
     int seg_k[4];
