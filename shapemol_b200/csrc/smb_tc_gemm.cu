@@ -22,6 +22,8 @@
 #include "smb_kernels.h"
 #include "smb_tc.cuh"
 
+#include <type_traits>
+
 namespace smb {
 
 namespace {
@@ -39,7 +41,7 @@ struct Cfg {
   static constexpr int W_BYTES = NT_MAX * KC * 2;
   static constexpr int STAGE_BYTES = SPLIT * (A_BYTES + W_BYTES);
   static constexpr int SBO = (KC / 8) * 128;
-  static constexpr int SMEM_TOTAL = 128 + 2 * STAGE_BYTES;
+  static constexpr int SMEM_TOTAL = 128 + NT_MAX * 4 + 2 * STAGE_BYTES;   // mbarriers | bias of the column tile | two stages
   static constexpr int N_TERMS = SPLIT == 3 ? 6 : 3;
 };
 
@@ -114,20 +116,22 @@ __global__ void __launch_bounds__(256) tc_wsplit_kernel(TcGemmArgs g, int n_chun
   }
 }
 
-template <int SPLIT>
+template <int SPLIT, bool IMG>
 __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   using C = Cfg<SPLIT>;
   constexpr int KC = C::KC, A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES, SBO = C::SBO;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);            // [0], [1]: stage free; [2]: all MMAs done; [3], [4]: stage full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
-  unsigned char* stages = smem + 128;
+  float* s_bias = reinterpret_cast<float*>(smem + 128);
+  unsigned char* stages = smem + 128 + NT_MAX * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * NT_MAX;
   const long long bz = blockIdx.z;
   const int n_left = g.N - n0;
   const int n_tile = n_left >= NT_MAX ? NT_MAX : (n_left + 15) & ~15;
 
+  for (int i = tid; i < NT_MAX; i += THREADS) s_bias[i] = (g.bias && blockIdx.y * NT_MAX + i < g.N) ? __ldg(g.bias + blockIdx.y * NT_MAX + i) : 0.f;
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid == 32) {
     mbar_init(bar + 0, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
@@ -176,10 +180,13 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
     }
   } else {
 
-  float4 ra[NA], rw[NW];                // this thread's pieces of the staged chunk (fp32)
-  const bool img = g.use_img != 0;      // W arrives pre-split through bulk copies
+  // this thread's pieces of the staged chunks (fp32).  Pre-split W (IMG): only A is staged by threads, and its gathered
+  // rows are fetched TWO chunks ahead (ncu: the first use of a prefetched piece was the kernel's top stall with one chunk).
+  constexpr int DEPTH = IMG ? 2 : 1;
+  float4 ra[DEPTH][NA], rw[IMG ? 1 : NW];
   int arow[NA], arow_seg = -1;          // gathered row of each of this thread's pieces in the current segment (-1: none)
-  auto fetch = [&](int c) {             // chunk c -> (segment, k0)
+  auto fetch = [&](int c, auto SLOT) {  // chunk c -> (segment, k0); registers of slot SLOT
+    constexpr int S = decltype(SLOT)::value;
     int s, k0;
     chunk_of(g, c, KC, s, k0);
     const TcGemmSeg& sg = g.seg[s];
@@ -193,24 +200,24 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
     }
 #pragma unroll
     for (int i = 0; i < NA; ++i)
-      ra[i] = arow[i] >= 0 ? load4(sg.a + bz * g.a_batch + (long long)arow[i] * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (img) return;
+      ra[S][i] = arow[i] >= 0 ? load4(sg.a + bz * g.a_batch + (long long)arow[i] * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (IMG) return;
     const float* wb = g.W + bz * g.w_batch + sg.w_off;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
+    for (int i = 0; i < (IMG ? 1 : NW); ++i) {
       const int n = sr + RSTEP * i;
       rw[i] = (n < n_tile && n0 + n < g.N) ? load4(wb + (long long)(n0 + n) * g.ldw, k0 + 4 * sp, sg.k, g.vec != 0)
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  if (n_chunks > 0) fetch(0);
   const int poff = (sp >> 1) * 128 + (sp & 1) * 8;    // piece position inside a K-major row
-  for (int c = 0; c < n_chunks; ++c) {
+  auto stage_chunk = [&](int c, auto SLOT) {
+    constexpr int S = decltype(SLOT)::value;
     const int st = c & 1;
     unsigned char* sa = stages + st * STAGE_BYTES;     // A pieces, then W pieces
     unsigned char* sw = sa + SPLIT * A_BYTES;
     if (c >= 2) mbar_wait(bar + st, ((c >> 1) - 1) & 1);   // the MMAs of chunk c - 2 have read this stage
-    if (img && tid == 0) {
+    if (IMG && tid == 0) {
       mbar_expect_tx(bar + 3 + st, SPLIT * W_BYTES);
       bulk_g2s(sw, reinterpret_cast<const unsigned char*>(g.w_img) + ((size_t)blockIdx.y * n_chunks + c) * (SPLIT * W_BYTES), SPLIT * W_BYTES,
                bar + 3 + st);
@@ -218,18 +225,26 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int r = sr + RSTEP * i;
-      split_store4<SPLIT>(ra[i], sa + (r >> 3) * SBO + (r & 7) * 16 + poff, A_BYTES);
+      split_store4<SPLIT>(ra[S][i], sa + (r >> 3) * SBO + (r & 7) * 16 + poff, A_BYTES);
     }
-    if (!img) {
+    if (!IMG) {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
+      for (int i = 0; i < (IMG ? 1 : NW); ++i) {
         const int n = sr + RSTEP * i;
         if (n < n_tile) split_store4<SPLIT>(rw[i], sw + (n >> 3) * SBO + (n & 7) * 16 + poff, W_BYTES);
       }
     }
-    if (c + 1 < n_chunks) fetch(c + 1);
+    if (c + DEPTH < n_chunks) fetch(c + DEPTH, SLOT);
     fence_async_smem();
     mbar_arrive(bar + 3 + st);
+  };
+  using I0 = std::integral_constant<int, 0>;
+  using I1 = std::integral_constant<int, DEPTH - 1>;
+  if (n_chunks > 0) fetch(0, I0{});
+  if (DEPTH > 1 && n_chunks > 1) fetch(1, I1{});
+  for (int c = 0; c < n_chunks; c += 2) {
+    stage_chunk(c, I0{});
+    if (c + 1 < n_chunks) stage_chunk(c + 1, I1{});
   }
   }   // staging warps
   if (n_chunks > 0) mbar_wait(bar + 2, 0);
@@ -249,16 +264,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
         for (int q = 0; q < 4; ++q) {
           const int n = cb + 4 * q;
           float o[4];
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.bias) {
-            if (g.vec_c && n0 + n + 3 < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + n));   // (vec_c: bias is 16-byte aligned too)
-            else {
-              if (n0 + n < g.N) b4.x = __ldg(g.bias + n0 + n);
-              if (n0 + n + 1 < g.N) b4.y = __ldg(g.bias + n0 + n + 1);
-              if (n0 + n + 2 < g.N) b4.z = __ldg(g.bias + n0 + n + 2);
-              if (n0 + n + 3 < g.N) b4.w = __ldg(g.bias + n0 + n + 3);
-            }
-          }
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n);   // staged once per CTA (zeros without a bias)
           o[0] = __uint_as_float(v[4 * q]) + b4.x; o[1] = __uint_as_float(v[4 * q + 1]) + b4.y;
           o[2] = __uint_as_float(v[4 * q + 2]) + b4.z; o[3] = __uint_as_float(v[4 * q + 3]) + b4.w;
           if (g.vec_c && n0 + n + 3 < g.N) {
@@ -317,12 +323,24 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
   }
   if (g.split3) {
     static size_t configured[kMaxDevices] = {};
-    if (int rc = ensure_dynamic_smem(tc_gemm_kernel<3>, Cfg<3>::SMEM_TOTAL, configured)) return rc;
-    tc_gemm_kernel<3><<<grid, THREADS, Cfg<3>::SMEM_TOTAL, st>>>(g);
+    static size_t configured_i[kMaxDevices] = {};
+    if (g.use_img) {
+      if (int rc = ensure_dynamic_smem(tc_gemm_kernel<3, true>, Cfg<3>::SMEM_TOTAL, configured_i)) return rc;
+      tc_gemm_kernel<3, true><<<grid, THREADS, Cfg<3>::SMEM_TOTAL, st>>>(g);
+    } else {
+      if (int rc = ensure_dynamic_smem(tc_gemm_kernel<3, false>, Cfg<3>::SMEM_TOTAL, configured)) return rc;
+      tc_gemm_kernel<3, false><<<grid, THREADS, Cfg<3>::SMEM_TOTAL, st>>>(g);
+    }
   } else {
     static size_t configured[kMaxDevices] = {};
-    if (int rc = ensure_dynamic_smem(tc_gemm_kernel<2>, Cfg<2>::SMEM_TOTAL, configured)) return rc;
-    tc_gemm_kernel<2><<<grid, THREADS, Cfg<2>::SMEM_TOTAL, st>>>(g);
+    static size_t configured_i[kMaxDevices] = {};
+    if (g.use_img) {
+      if (int rc = ensure_dynamic_smem(tc_gemm_kernel<2, true>, Cfg<2>::SMEM_TOTAL, configured_i)) return rc;
+      tc_gemm_kernel<2, true><<<grid, THREADS, Cfg<2>::SMEM_TOTAL, st>>>(g);
+    } else {
+      if (int rc = ensure_dynamic_smem(tc_gemm_kernel<2, false>, Cfg<2>::SMEM_TOTAL, configured)) return rc;
+      tc_gemm_kernel<2, false><<<grid, THREADS, Cfg<2>::SMEM_TOTAL, st>>>(g);
+    }
   }
   return (int)cudaGetLastError();
 }
