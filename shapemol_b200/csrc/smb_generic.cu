@@ -110,6 +110,64 @@ __global__ void __launch_bounds__(128) attn_alpha_kernel(const float* __restrict
   }
 }
 
+// Same, for hidden widths that are multiples of 128 with 4 | dh | 128: a warp reads every key row with coalesced 16-byte loads (lane =
+// four consecutive channels of each 128-channel piece), the dh / 4 lanes of a head reduce with shuffles, logits go through shared
+// memory [slot][head], and lane h does the softmax of head h.  (The kernel above reads a row 4 bytes at a time per (head, slot).)
+template <int PIECES>
+__global__ void __launch_bounds__(128) attn_alpha_rows_kernel(const float* __restrict__ q, const float* __restrict__ kbuf, const int* __restrict__ deg,
+                                                              int n_atoms, int KS, int heads, float* __restrict__ alpha) {
+  extern __shared__ float s_logit[];                      // [4 warps][KS][heads]
+  constexpr int Hd = PIECES * 128;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + w;
+  if (i >= n_atoms) return;
+  const int dg = deg[i], dh = Hd / heads, lph = dh / 4;   // lanes per head
+  const float scale = 1.f / sqrtf((float)dh);
+  float* lg = s_logit + (size_t)w * KS * heads;
+  float4 q4[PIECES];
+#pragma unroll
+  for (int p = 0; p < PIECES; ++p) q4[p] = __ldg(reinterpret_cast<const float4*>(q + (size_t)i * Hd + p * 128) + lane);
+  const float4* krow = reinterpret_cast<const float4*>(kbuf + (size_t)i * KS * Hd) + lane;
+  for (int s = 0; s < dg; ++s) {
+    float part[PIECES];
+#pragma unroll
+    for (int p = 0; p < PIECES; ++p) {
+      const float4 k4 = __ldg(krow + (size_t)s * (Hd / 4) + p * 32);
+      part[p] = fmaf(q4[p].x, k4.x, fmaf(q4[p].y, k4.y, fmaf(q4[p].z, k4.z, q4[p].w * k4.w)));
+    }
+#pragma unroll
+    for (int p = 0; p < PIECES; ++p) {
+      float v = part[p];
+      for (int o = 1; o < lph; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane % lph == 0) lg[s * heads + p * (128 / dh) + lane / lph] = v * scale;
+    }
+  }
+  __syncwarp();
+  for (int h = lane; h < heads; h += 32) {
+    float mx = -INFINITY;
+    for (int s = 0; s < dg; ++s) mx = fmaxf(mx, lg[s * heads + h]);
+    float sum = 0.f;
+    for (int s = 0; s < dg; ++s) sum += expf(lg[s * heads + h] - mx);
+    const float inv = 1.f / sum;
+    for (int s = 0; s < dg; ++s) alpha[((size_t)i * KS + s) * heads + h] = expf(lg[s * heads + h] - mx) * inv;
+  }
+}
+
+int launch_attn_alpha(const float* q, const float* kbuf, const int* deg, int N, int KS, int Hd, int heads, float* alpha, cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int dh = heads > 0 ? Hd / heads : 0;
+  const size_t smem = (size_t)4 * KS * heads * sizeof(float);
+  const bool rows = Hd % 128 == 0 && Hd <= 512 && dh >= 4 && dh <= 128 && (dh & (dh - 1)) == 0 && smem <= 48 * 1024 &&
+                    (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kbuf) & 15) == 0;
+  const unsigned grid = (unsigned)((N + 3) / 4);
+  if (rows && Hd == 128) attn_alpha_rows_kernel<1><<<grid, 128, smem, st>>>(q, kbuf, deg, N, KS, heads, alpha);
+  else if (rows && Hd == 256) attn_alpha_rows_kernel<2><<<grid, 128, smem, st>>>(q, kbuf, deg, N, KS, heads, alpha);
+  else if (rows && Hd == 384) attn_alpha_rows_kernel<3><<<grid, 128, smem, st>>>(q, kbuf, deg, N, KS, heads, alpha);
+  else if (rows && Hd == 512) attn_alpha_rows_kernel<4><<<grid, 128, smem, st>>>(q, kbuf, deg, N, KS, heads, alpha);
+  else attn_alpha_kernel<<<grid, 128, 0, st>>>(q, kbuf, deg, N, KS, Hd, heads, alpha);
+  return (int)cudaGetLastError();
+}
+
 // ---- X2H aggregation: agg[i][c] = sum_s alpha[e][head(c)] e_w[e] v[e][c]  (uni_transformer.py:69-81) ---------------------
 __global__ void __launch_bounds__(256) agg_v_kernel(const float* __restrict__ alpha, const float* __restrict__ ew, const float* __restrict__ vbuf,
                                                     const int* __restrict__ deg, int n_atoms, int KS, int Hd, int heads, float* __restrict__ agg) {
@@ -322,8 +380,7 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
     // ---- X2H (uni_transformer.py:48-90) ----
     SMB_G(edge_mlp(x2h + ".hk_func", h_in, H, gout));
     SMB_G(node_mlp(x2h + ".hq_func", h_in, q));
-    attn_alpha_kernel<<<(N + 3) / 4, 128, 0, st>>>(q, gout, deg, N, KS, H, heads, galpha);
-    SMB_G((int)cudaGetLastError());
+    SMB_G(launch_attn_alpha(q, gout, deg, N, KS, H, heads, galpha, st));
     SMB_G(edge_mlp(x2h + ".hv_func", h_in, H, gout));
     agg_v_kernel<<<(unsigned)(((size_t)N * H + 255) / 256), 256, 0, st>>>(galpha, ew, gout, deg, N, KS, H, heads, agg);
     SMB_G((int)cudaGetLastError());
@@ -339,8 +396,7 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
     // ---- H2X on the updated h (uni_transformer.py:121-162) ----
     SMB_G(edge_mlp(h2x + ".xk_func", h_out, H, gout));
     SMB_G(node_mlp(h2x + ".xq_func", h_out, q));
-    attn_alpha_kernel<<<(N + 3) / 4, 128, 0, st>>>(q, gout, deg, N, KS, H, heads, galpha);
-    SMB_G((int)cudaGetLastError());
+    SMB_G(launch_attn_alpha(q, gout, deg, N, KS, H, heads, galpha, st));
     SMB_G(edge_mlp(h2x + ".xv_func", h_out, heads, gout));
     xv_vn_kernel<<<(N + 3) / 4, 128, 0, st>>>(galpha, ew, gout, grel, deg, b.atom_mol, x, io.shape,
                                               P(h2x + ".shape_linear.map_to_feat.weight"), P(h2x + ".shape_linear.map_to_dir.weight"), N, KS, vn, gbn);

@@ -258,13 +258,16 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
     for (int cb = (warp >> 2) * 16; cb < n_tile; cb += 32) {
       uint32_t v[16];
       tmem_ld16(lane_addr + cb, v);
+      float4 bq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bq[q] = *reinterpret_cast<const float4*>(s_bias + cb + 4 * q);   // staged once per CTA (zeros without a bias)
       wait_ld();
       if (m < g.M) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int n = cb + 4 * q;
           float o[4];
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n);   // staged once per CTA (zeros without a bias)
+          const float4 b4 = bq[q];
           o[0] = __uint_as_float(v[4 * q]) + b4.x; o[1] = __uint_as_float(v[4 * q + 1]) + b4.y;
           o[2] = __uint_as_float(v[4 * q + 2]) + b4.z; o[3] = __uint_as_float(v[4 * q + 3]) + b4.w;
           if (g.vec_c && n0 + n + 3 < g.N) {
