@@ -232,8 +232,10 @@ struct Seg { const float* a; const int* idx; int lda; int k; };
 // scratch for the pre-split weight image of the GEMM in flight: part of the calling forward's workspace (stream-ordered reuse)
 thread_local void* t_wimg = nullptr;
 thread_local long long t_wimg_bytes = 0;
+int row_act(float* X, int M, int Hd, const float* g, const float* b, int act, cudaStream_t st);
+// ln_g / ln_b: LayerNorm -> ReLU of the output rows, fused into the GEMM's epilogue when the whole row is in one column tile
 int gemm_cat(const Seg* segs, int n_segs, const float* W, int ldw, int M, int N, const float* bias, bool accumulate, float* C, int ldc,
-             cudaStream_t st) {
+             cudaStream_t st, const float* ln_g = nullptr, const float* ln_b = nullptr) {
   TcGemmArgs g;
   memset(&g, 0, sizeof(g));
   int off = 0;
@@ -243,12 +245,15 @@ int gemm_cat(const Seg* segs, int n_segs, const float* W, int ldw, int M, int N,
   }
   g.n_segs = n_segs; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.bias = bias; g.accumulate = accumulate ? 1 : 0; g.C = C; g.ldc = ldc;
   g.w_img = t_wimg; g.w_img_bytes = t_wimg_bytes;
-  return launch_tc_gemm(g, 1, st);
+  const bool fuse = ln_g && ln_b && ldc == N && tc_gemm_can_fuse_ln(N, accumulate);
+  if (fuse) { g.ln_gamma = ln_g; g.ln_beta = ln_b; }
+  if (int rc = launch_tc_gemm(g, 1, st)) return rc;
+  return (ln_g && ln_b && !fuse) ? row_act(C, M, N, ln_g, ln_b, ACT_LN_RELU, st) : 0;
 }
 int gemm(const float* A, const int* a_idx, int lda, const float* W, int ldw, int M, int N, int K, const float* bias, bool accumulate,
-         float* C, int ldc, cudaStream_t st) {
+         float* C, int ldc, cudaStream_t st, const float* ln_g = nullptr, const float* ln_b = nullptr) {
   const Seg sg = {A, a_idx, lda, K};
-  return gemm_cat(&sg, 1, W, ldw, M, N, bias, accumulate, C, ldc, st);
+  return gemm_cat(&sg, 1, W, ldw, M, N, bias, accumulate, C, ldc, st, ln_g, ln_b);
 }
 int row_act(float* X, int M, int Hd, const float* g, const float* b, int act, cudaStream_t st) {
   if (M <= 0) return 0;
@@ -348,14 +353,13 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
     const float* w0 = P(p + ".net.0.weight");
     // kv = [r | h_dst | h_src | inv_dst] (uni_transformer.py:61-63) as ONE gathered GEMM over the concatenated operand
     const Seg kv[4] = {{grbf, nullptr, kRbf, kRbf}, {h, dst_idx, H, H}, {h, src_idx, H, H}, {inv, mol_idx, kShape, kShape}};
-    SMB_G(gemm_cat(kv, 4, w0, KV, M, H, P(p + ".net.0.bias"), false, ghid, H, st));
-    SMB_G(row_act(ghid, M, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
+    SMB_G(gemm_cat(kv, 4, w0, KV, M, H, P(p + ".net.0.bias"), false, ghid, H, st, P(p + ".net.1.weight"), P(p + ".net.1.bias")));
     SMB_G(gemm(ghid, nullptr, H, P(p + ".net.3.weight"), H, M, n2, H, P(p + ".net.3.bias"), false, out, n2, st));
     return 0;
   };
   auto node_mlp = [&](const std::string& p, const float* h, float* out) -> int {   // hq_func / xq_func
-    SMB_G(gemm(h, nullptr, H, P(p + ".net.0.weight"), H, N, H, H, P(p + ".net.0.bias"), false, gnode, H, st));
-    SMB_G(row_act(gnode, N, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
+    SMB_G(gemm(h, nullptr, H, P(p + ".net.0.weight"), H, N, H, H, P(p + ".net.0.bias"), false, gnode, H, st, P(p + ".net.1.weight"),
+               P(p + ".net.1.bias")));
     SMB_G(gemm(gnode, nullptr, H, P(p + ".net.3.weight"), H, N, H, H, P(p + ".net.3.bias"), false, out, H, st));
     return 0;
   };
@@ -364,8 +368,8 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
   SMB_G(geom());
   {
     const std::string p = "refine_net.edge_pred_layer";
-    SMB_G(gemm(grbf, nullptr, kRbf, P(p + ".net.0.weight"), kRbf, M, H, kRbf, P(p + ".net.0.bias"), false, ghid, H, st));
-    SMB_G(row_act(ghid, M, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
+    SMB_G(gemm(grbf, nullptr, kRbf, P(p + ".net.0.weight"), kRbf, M, H, kRbf, P(p + ".net.0.bias"), false, ghid, H, st, P(p + ".net.1.weight"),
+               P(p + ".net.1.bias")));
     gate_dot_kernel<<<(M + 3) / 4, 128, 0, st>>>(ghid, M, H, P(p + ".net.3.weight"), P(p + ".net.3.bias"), ew);
     SMB_G((int)cudaGetLastError());
   }
@@ -388,8 +392,7 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
       const std::string p = x2h + ".node_output";
       const float* w0 = P(p + ".net.0.weight");
       const Seg cat[2] = {{agg, nullptr, H, H}, {h_in, nullptr, H, H}};     // [agg | h] (uni_transformer.py:82)
-      SMB_G(gemm_cat(cat, 2, w0, 2 * H, N, H, P(p + ".net.0.bias"), false, gnode, H, st));
-      SMB_G(row_act(gnode, N, H, P(p + ".net.1.weight"), P(p + ".net.1.bias"), ACT_LN_RELU, st));
+      SMB_G(gemm_cat(cat, 2, w0, 2 * H, N, H, P(p + ".net.0.bias"), false, gnode, H, st, P(p + ".net.1.weight"), P(p + ".net.1.bias")));
       SMB_CUDA_OK(cudaMemcpyAsync(h_out, h_in, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, st));   // residual (:87-88)
       SMB_G(gemm(gnode, nullptr, H, P(p + ".net.3.weight"), H, N, H, H, P(p + ".net.3.bias"), true, h_out, H, st));
     }

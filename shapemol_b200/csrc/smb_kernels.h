@@ -173,7 +173,11 @@ struct TcGemmArgs {
   void* w_img;
   long long w_img_bytes;
   int use_img;         // set by the launcher
+  // optional fused epilogue: y = relu(LayerNorm(C row) * ln_gamma + ln_beta) (eps 1e-5) instead of the plain row -- the Linear ->
+  // LayerNorm -> ReLU head of the reference's MLP (models/common.py:47-67).  Needs N <= 256, N % 16 == 0, no accumulate.
+  const float* ln_gamma; const float* ln_beta;
 };
+bool tc_gemm_can_fuse_ln(int N, bool accumulate);
 long long tc_gemm_w_img_bytes(int N, const int* seg_k, int n_segs, bool split3);   // scratch needed for TcGemmArgs::w_img
 int launch_tc_gemm(const TcGemmArgs& g, int n_batch, cudaStream_t st);
 

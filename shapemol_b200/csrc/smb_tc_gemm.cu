@@ -41,7 +41,7 @@ struct Cfg {
   static constexpr int W_BYTES = NT_MAX * KC * 2;
   static constexpr int STAGE_BYTES = SPLIT * (A_BYTES + W_BYTES);
   static constexpr int SBO = (KC / 8) * 128;
-  static constexpr int SMEM_TOTAL = 128 + NT_MAX * 4 + 2 * STAGE_BYTES;   // mbarriers | bias of the column tile | two stages
+  static constexpr int SMEM_TOTAL = 128 + 4 * NT_MAX * 4 + 2 * STAGE_BYTES;   // mbarriers | bias, LN gamma, LN beta of the column tile, LN partial sums | two stages
   static constexpr int N_TERMS = SPLIT == 3 ? 6 : 3;
 };
 
@@ -124,14 +124,22 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);            // [0], [1]: stage free; [2]: all MMAs done; [3], [4]: stage full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
   float* s_bias = reinterpret_cast<float*>(smem + 128);
-  unsigned char* stages = smem + 128 + NT_MAX * 4;
+  float* s_gamma = s_bias + NT_MAX;
+  float* s_beta = s_gamma + NT_MAX;
+  float* s_red = s_beta + NT_MAX;      // [2 column halves][128 rows]
+  unsigned char* stages = smem + 128 + 4 * NT_MAX * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * NT_MAX;
   const long long bz = blockIdx.z;
   const int n_left = g.N - n0;
   const int n_tile = n_left >= NT_MAX ? NT_MAX : (n_left + 15) & ~15;
 
-  for (int i = tid; i < NT_MAX; i += THREADS) s_bias[i] = (g.bias && blockIdx.y * NT_MAX + i < g.N) ? __ldg(g.bias + blockIdx.y * NT_MAX + i) : 0.f;
+  for (int i = tid; i < NT_MAX; i += THREADS) {
+    const bool in = blockIdx.y * NT_MAX + i < g.N;
+    s_bias[i] = (g.bias && in) ? __ldg(g.bias + blockIdx.y * NT_MAX + i) : 0.f;
+    s_gamma[i] = (g.ln_gamma && in) ? __ldg(g.ln_gamma + i) : 0.f;
+    s_beta[i] = (g.ln_gamma && in) ? __ldg(g.ln_beta + i) : 0.f;
+  }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid == 32) {
     mbar_init(bar + 0, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
@@ -255,6 +263,31 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
     const int row = (warp & 3) * 32 + lane, m = m0 + row;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* crow = g.C + bz * g.c_batch + (long long)m * g.ldc + n0;
+    // fused LayerNorm (the whole row is in this CTA's accumulator: N <= 256): the row's two threads -- the warps of a TMEM lane
+    // quadrant alternate 16-column chunks -- exchange partial sums through shared memory; mean, then centred sum of squares
+    // (two more passes over TMEM), like the separate row kernel it replaces
+    float mean = 0.f, rstd = 1.f;
+    if (g.ln_gamma) {
+      const int half = warp >> 2;
+      auto row_sum = [&](auto f) {
+        float acc = 0.f;
+        for (int cb = half * 16; cb < n_tile; cb += 32) {
+          uint32_t v[16];
+          tmem_ld16(lane_addr + cb, v);
+          wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc = f(acc, __uint_as_float(v[e]) + s_bias[cb + e]);
+        }
+        s_red[half * TM + row] = acc;
+        named_sync(1 + (warp & 3), 64);
+        const float tot = acc + s_red[(half ^ 1) * TM + row];
+        named_sync(1 + (warp & 3), 64);       // both threads have read before the next pass overwrites
+        return tot;
+      };
+      mean = row_sum([](float a, float x) { return a + x; }) / (float)g.N;
+      const float m_ = mean;
+      rstd = 1.f / sqrtf(row_sum([m_](float a, float x) { const float d = x - m_; return fmaf(d, d, a); }) / (float)g.N + 1e-5f);
+    }
     for (int cb = (warp >> 2) * 16; cb < n_tile; cb += 32) {
       uint32_t v[16];
       tmem_ld16(lane_addr + cb, v);
@@ -270,6 +303,11 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
           const float4 b4 = bq[q];
           o[0] = __uint_as_float(v[4 * q]) + b4.x; o[1] = __uint_as_float(v[4 * q + 1]) + b4.y;
           o[2] = __uint_as_float(v[4 * q + 2]) + b4.z; o[3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+          if (g.ln_gamma) {
+            const float4 ga = *reinterpret_cast<const float4*>(s_gamma + n), be = *reinterpret_cast<const float4*>(s_beta + n);
+            o[0] = fmaxf(fmaf((o[0] - mean) * rstd, ga.x, be.x), 0.f); o[1] = fmaxf(fmaf((o[1] - mean) * rstd, ga.y, be.y), 0.f);
+            o[2] = fmaxf(fmaf((o[2] - mean) * rstd, ga.z, be.z), 0.f); o[3] = fmaxf(fmaf((o[3] - mean) * rstd, ga.w, be.w), 0.f);
+          }
           if (g.vec_c && n0 + n + 3 < g.N) {
             float4* dst = reinterpret_cast<float4*>(crow + n);
             if (g.accumulate) { const float4 p = *dst; o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w; }
@@ -292,6 +330,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+bool tc_gemm_can_fuse_ln(int N, bool accumulate) { return N <= NT_MAX && N % 16 == 0 && !accumulate; }
+
 long long tc_gemm_w_img_bytes(int N, const int* seg_k, int n_segs, bool split3) {
   const int KC = split3 ? Cfg<3>::KC : Cfg<2>::KC;
   long long chunks = 0;
@@ -303,6 +343,10 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
   if (g_in.M <= 0 || g_in.N <= 0 || n_batch <= 0) return 0;
   if (g_in.n_segs < 1 || g_in.n_segs > 4) { set_error_msg("tc_gemm: 1..4 operand segments"); return SMB_E_BADARG; }
   TcGemmArgs g = g_in;
+  if ((g.ln_gamma != nullptr) != (g.ln_beta != nullptr) || (g.ln_gamma && !tc_gemm_can_fuse_ln(g.N, g.accumulate != 0))) {
+    set_error_msg("tc_gemm: the fused LayerNorm needs gamma and beta, N <= 256, N % 16 == 0 and no accumulate");
+    return SMB_E_BADARG;
+  }
   // 16-byte vector loads / stores only where every row start is 16-byte aligned
   bool vec = aligned16(g.W) && g.ldw % 4 == 0 && g.w_batch % 4 == 0;
   for (int s = 0; s < g.n_segs; ++s)
