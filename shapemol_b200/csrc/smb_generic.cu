@@ -414,7 +414,12 @@ int forward_generic(const smb_model_dims& d, const void* blob, const ModelLayout
     SMB_G(launch_vn_apply(vn, bn_param, x, last ? io.pred_pos : nullptr, N, st));
     cur ^= 1;
   }
-  return type_head_generic(d, blob, L, N, io.pred_h, io.pred_v, st);
+  // type head v_inference: Linear -> shifted softplus -> Linear (molopt_score_model.py:262-266,305) as two tensor-core GEMMs
+  // (type_head_generic below -- one CTA per atom, no scratch -- serves the scratch-free smb_type_head entry point)
+  SMB_G(gemm(io.pred_h, nullptr, H, P("v_inference.0.weight"), H, N, H, H, P("v_inference.0.bias"), false, gnode, H, st));
+  SMB_G(row_act(gnode, N, H, nullptr, nullptr, ACT_SSP, st));
+  SMB_G(gemm(gnode, nullptr, H, P("v_inference.2.weight"), H, N, d.classes, H, P("v_inference.2.bias"), false, io.pred_v, d.classes, st));
+  return 0;
 }
 
 // v_inference: Linear -> shifted softplus -> Linear (molopt_score_model.py:262-266,305); one CTA per atom, no scratch
