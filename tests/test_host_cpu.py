@@ -148,3 +148,22 @@ def test_dropin_shape_autoencoder_state_dict_matches_reference():
     assert len(ae.encoder.blocks) == 4 and not any(k.startswith('encoder.blocks') for k in sd)
     with pytest.raises(Exception):
         ae.encoder(torch.zeros(1, 1, 64, 3))     # CPU tensor: the encoder has no CPU path
+
+
+def test_tile_walk_host_mirror():
+    """bench.tiles_and_rows mirrors the device tile walk (csrc/smb_edge_ws.cu TileWalk): 27-atom molecules give 7 whole-destination
+    tiles (104 of 128 rows) or 6 split tiles (117 rows); splitting never needs more tiles; every edge slot is covered once."""
+    import importlib
+    bench = importlib.import_module('bench')
+    s27 = torch.full((10,), 27)
+    assert bench.tiles_and_rows(s27, 32, split=False) == (70, 10 * 27 * 26)
+    assert bench.tiles_and_rows(s27, 32, split=True) == (60, 10 * 27 * 26)
+    g = torch.Generator().manual_seed(3)
+    for k in (3, 8, 12, 20, 32, 48):
+        sizes = torch.randint(1, 33, (200,), generator=g)
+        ts, rs = bench.tiles_and_rows(sizes, k, split=True)
+        tw, rw = bench.tiles_and_rows(sizes, k, split=False)
+        deg = torch.clamp(sizes - 1, max=k)
+        assert rs == rw == int((sizes * deg).sum())
+        assert ts <= tw
+        assert ts * 128 >= rs
