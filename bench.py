@@ -96,16 +96,20 @@ def tiles_and_rows(sizes, k, split=True):
             else:
                 E = n * deg
                 nt = (E + 127) // 128
-                target = (E + nt - 1) // nt if split else min(128 // deg, 8) * deg
-                e, cnt = 0, 0
-                while e < E:
-                    r = min(target, E - e)
-                    d0 = e // deg
-                    if (e + r - 1) // deg - d0 + 1 > 8:
-                        r = (d0 + 8) * deg - e
-                    e += r
-                    cnt += 1
-                cache[n] = (cnt, E)
+
+                def walk(sp):
+                    target = (E + nt - 1) // nt if sp else min(128 // deg, 8) * deg
+                    e, cnt = 0, 0
+                    while e < E:
+                        r = min(target, E - e)
+                        d0 = e // deg
+                        if (e + r - 1) // deg - d0 + 1 > 8:
+                            r = (d0 + 8) * deg - e
+                        e += r
+                        cnt += 1
+                    return cnt
+                whole = walk(False)
+                cache[n] = (min(whole, walk(True)) if split else whole, E)   # split only where it saves a tile
         tiles += cache[n][0]
         rows += cache[n][1]
     return tiles, rows

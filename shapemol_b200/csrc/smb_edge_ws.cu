@@ -1074,13 +1074,18 @@ struct TileWalk {
     e += rows;
   }
 };
-__device__ __forceinline__ int tiles_of(int n, int k, bool split) {
-  if (n <= 0) return 0;
-  if (min(k, n - 1) == 0) return 1;
+__device__ __forceinline__ int tiles_of_walk(int n, int k, bool split) {
   TileWalk w(n, k, split);
   int cnt = 0, e0, rows, d0, nd;
   while (!w.done()) { w.next(e0, rows, d0, nd); ++cnt; }
   return cnt;
+}
+// a molecule's tiles split destinations only where that saves a tile (with the 8-part cap an equal run can even need one more)
+__device__ __forceinline__ bool split_pays(int n, int k) { return tiles_of_walk(n, k, true) < tiles_of_walk(n, k, false); }
+__device__ __forceinline__ int tiles_of(int n, int k, bool split) {
+  if (n <= 0) return 0;
+  if (min(k, n - 1) == 0) return 1;
+  return tiles_of_walk(n, k, split && split_pays(n, k));
 }
 
 __global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict__ mol_ptr, int n_mols, int k, int split, int4* __restrict__ tiles,
@@ -1117,7 +1122,7 @@ __global__ void __launch_bounds__(1024) build_tiles_kernel(const int* __restrict
     const int deg = min(k, n - 1);
     if (deg == 0) { tiles[off++] = make_int4(a0, m, n | (1 << 16), 0); continue; }   // single atom: one empty tile
     const int recip = 65536 / deg + 1;
-    TileWalk w(n, k, split != 0);
+    TileWalk w(n, k, split != 0 && split_pays(n, k));
     while (!w.done()) {
       int e0, rows, d0, nd;
       w.next(e0, rows, d0, nd);
