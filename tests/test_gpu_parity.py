@@ -266,7 +266,9 @@ def test_trajectory_free_running_bf16_mode(cuda_lib):
 
 @pytest.mark.parametrize('k,sizes', [(4, [30, 17, 5, 32, 21]), (3, [20, 31]), (12, [14, 32, 9, 27]),
                                      # degrees 17..31: every way a split tile of the gate / H2X block can begin and end inside a destination
-                                     (32, list(range(18, 33)) + [2, 1, 27, 27]), (20, [32, 21, 22, 26, 19, 30]), (25, [26, 27, 31, 32])])
+                                     (32, list(range(18, 33)) + [2, 1, 27, 27]), (20, [32, 21, 22, 26, 19, 30]), (25, [26, 27, 31, 32]),
+                                     # a molecule of more than 32 atoms: the bf16 mode falls back to the mma.sync kernels for the whole batch
+                                     (32, [45, 17, 60, 33, 8])])
 def test_bf16_small_k_many_destinations_per_tile(cuda_lib, k, sizes):
     """Small k with molecules of 17..32 atoms: many destinations share a 128-row tile (the per-tile destination cap); larger k:
     tiles that split destinations (two parts combined through their softmax statistics, smb_edge_ws.cu).
