@@ -326,6 +326,218 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(TcGemmArgs g) {
   if (warp == 0) tmem_free<256>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Persistent variant for big GEMMs with a pre-split shared W and N <= 256 (one column tile): one CTA per SM walks the 128-row
+// tiles; the accumulator is double-buffered in TMEM (2 x 256 columns) and the epilogue has its own eight warps, so the epilogue
+// of tile t (with the fused LayerNorm: three passes over TMEM plus the stores -- half of a tile's time in the kernel above, where
+// the two co-resident CTAs run in lockstep) overlaps the main loop of tile t + 1.  Four-stage operand ring: the staging warps run up
+// to four chunks ahead of the MMA issuer, which also hides the latency of W's bulk copies.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 4, P_EPI = 256, P_THREADS = STAGERS + 32 + P_EPI;
+template <int SPLIT>
+struct PCfg {
+  static constexpr int SMEM_TOTAL = 256 + 4 * NT_MAX * 4 + P_STAGES * Cfg<SPLIT>::STAGE_BYTES;
+};
+enum { PB_FULL = 0, PB_FREE = 4, PB_ACC_FULL = 8, PB_ACC_FREE = 10, PB_N = 12 };
+
+template <int SPLIT>
+__global__ void __launch_bounds__(P_THREADS, 1) tc_gemm_persistent_kernel(TcGemmArgs g) {
+  using C = Cfg<SPLIT>;
+  constexpr int KC = C::KC, A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES, SBO = C::SBO;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
+  float* s_bias = reinterpret_cast<float*>(smem + 256);
+  float* s_gamma = s_bias + NT_MAX;
+  float* s_beta = s_gamma + NT_MAX;
+  float* s_red = s_beta + NT_MAX;      // [2 column halves][128 rows]
+  unsigned char* stages = smem + 256 + 4 * NT_MAX * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tile = g.N >= NT_MAX ? NT_MAX : (g.N + 15) & ~15;
+  const int n_row_tiles = (g.M + TM - 1) / TM;
+  int n_chunks = 0;
+  for (int s = 0; s < g.n_segs; ++s) n_chunks += (g.seg[s].k + KC - 1) / KC;
+
+  for (int i = tid; i < NT_MAX; i += P_THREADS) {
+    const bool in = i < g.N;
+    s_bias[i] = (g.bias && in) ? __ldg(g.bias + i) : 0.f;
+    s_gamma[i] = (g.ln_gamma && in) ? __ldg(g.ln_gamma + i) : 0.f;
+    s_beta[i] = (g.ln_gamma && in) ? __ldg(g.ln_beta + i) : 0.f;
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid == 32) {
+    for (int b = 0; b < P_STAGES; ++b) { mbar_init(bar + PB_FULL + b, STAGERS); mbar_init(bar + PB_FREE + b, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar + PB_ACC_FULL + b, 1); mbar_init(bar + PB_ACC_FREE + b, P_EPI); }
+    mbar_init_fence();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = idesc_bf16(n_tile, false);
+
+  if (warp < STAGERS / 32) {
+    // =========================== A staging (the map of tc_gemm_kernel) + W bulk copies ===========================
+    constexpr int PPR = KC / 4, RSTEP = STAGERS / PPR, NA = TM / RSTEP;
+    const int sp = tid % PPR, sr = tid / PPR;
+    const int poff = (sp >> 1) * 128 + (sp & 1) * 8;
+    float4 ra[2][NA];
+    int arow[NA], arow_seg;
+    int gc = 0;                                  // chunks staged so far (all tiles): ring position
+    for (int tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+      const int m0 = tile * TM;
+      arow_seg = -1;
+      auto fetch = [&](int c, auto SLOT) {
+        constexpr int S = decltype(SLOT)::value;
+        int s, k0;
+        chunk_of(g, c, KC, s, k0);
+        const TcGemmSeg& sg = g.seg[s];
+        if (s != arow_seg) {
+          arow_seg = s;
+#pragma unroll
+          for (int i = 0; i < NA; ++i) {
+            const int m = m0 + sr + RSTEP * i;
+            arow[i] = m < g.M ? (sg.idx ? __ldg(sg.idx + m) : m) : -1;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+          ra[S][i] = arow[i] >= 0 ? load4(sg.a + (long long)arow[i] * sg.lda, k0 + 4 * sp, sg.k, g.vec != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto stage_chunk = [&](int c, auto SLOT) {
+        constexpr int S = decltype(SLOT)::value;
+        const int st = gc % P_STAGES;
+        unsigned char* sa = stages + st * STAGE_BYTES;
+        unsigned char* sw = sa + SPLIT * A_BYTES;
+        if (gc >= P_STAGES) mbar_wait(bar + PB_FREE + st, ((gc / P_STAGES) - 1) & 1);   // the MMAs of the chunk P_STAGES back have read this stage
+        if (tid == 0) {
+          mbar_expect_tx(bar + PB_FULL + st, SPLIT * W_BYTES);
+          bulk_g2s(sw, reinterpret_cast<const unsigned char*>(g.w_img) + (size_t)c * (SPLIT * W_BYTES), SPLIT * W_BYTES, bar + PB_FULL + st);
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const int r = sr + RSTEP * i;
+          split_store4<SPLIT>(ra[S][i], sa + (r >> 3) * SBO + (r & 7) * 16 + poff, A_BYTES);
+        }
+        if (c + 2 < n_chunks) fetch(c + 2, SLOT);
+        fence_async_smem();
+        mbar_arrive(bar + PB_FULL + st);
+        ++gc;
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      if (n_chunks > 0) fetch(0, I0{});
+      if (n_chunks > 1) fetch(1, I1{});
+      for (int c = 0; c < n_chunks; c += 2) {
+        stage_chunk(c, I0{});
+        if (c + 1 < n_chunks) stage_chunk(c + 1, I1{});
+      }
+    }
+  } else if (warp == STAGERS / 32) {
+    // =========================== MMA issuer ===========================
+    int gc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      if (it >= 2) mbar_wait<32>(bar + PB_ACC_FREE + ab, ((it >> 1) - 1) & 1);   // the epilogue of tile it - 2 has drained this accumulator
+      fence_after_sync();
+      const uint32_t d = tmem + (uint32_t)ab * NT_MAX;
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c, ++gc) {
+        const int st = gc % P_STAGES;
+        mbar_wait<32>(bar + PB_FULL + st, (gc / P_STAGES) & 1);
+        fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a0 = smem_u32(stages + st * STAGE_BYTES), w0 = a0 + SPLIT * A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+#pragma unroll
+            for (int t = 0; t < C::N_TERMS; ++t) {
+              const int pa = SPLIT == 3 ? (t == 1 || t == 3 ? 1 : t == 5 ? 2 : 0) : (t == 1 ? 1 : 0);
+              const int pw = SPLIT == 3 ? (t == 2 || t == 3 ? 1 : t == 4 ? 2 : 0) : (t == 2 ? 1 : 0);
+              mma_ss(d, smem_desc(a0 + pa * A_BYTES + ks * 256, 128, SBO), smem_desc(w0 + pw * W_BYTES + ks * 256, 128, SBO), idesc,
+                     (c | ks | t) > 0);
+            }
+          mma_commit(bar + PB_FREE + st);
+          if (c + 1 == n_chunks) mma_commit(bar + PB_ACC_FULL + ab);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue warps: thread = (row, 16-column chunks of one parity) ===========================
+    const int ew = warp - (STAGERS / 32 + 1);          // 0..7
+    const int qd = warp & 3, half = ew >> 2 & 1;       // TMEM lane quadrant = warp id mod 4
+    // the two warps of a quadrant must differ in `half`: ew and ew ^ 4 share (warp & 3)
+    const int row = qd * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1, m = tile * TM + row;
+      mbar_wait(bar + PB_ACC_FULL + ab, (it >> 1) & 1);
+      fence_after_sync();
+      const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)ab * NT_MAX;
+      float* crow = g.C + (long long)m * g.ldc;
+      float mean = 0.f, rstd = 1.f;
+      if (g.ln_gamma) {
+        auto row_sum = [&](auto f) {
+          float acc = 0.f;
+          for (int cb = half * 16; cb < n_tile; cb += 32) {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + cb, v);
+            wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc = f(acc, __uint_as_float(v[e]) + s_bias[cb + e]);
+          }
+          s_red[half * TM + row] = acc;
+          named_sync(1 + qd, 64);
+          const float tot = acc + s_red[(half ^ 1) * TM + row];
+          named_sync(1 + qd, 64);
+          return tot;
+        };
+        mean = row_sum([](float a, float x) { return a + x; }) / (float)g.N;
+        const float m_ = mean;
+        rstd = 1.f / sqrtf(row_sum([m_](float a, float x) { const float dd = x - m_; return fmaf(dd, dd, a); }) / (float)g.N + 1e-5f);
+      }
+      for (int cb = half * 16; cb < n_tile; cb += 32) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + cb, v);
+        float4 bq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bq[q] = *reinterpret_cast<const float4*>(s_bias + cb + 4 * q);
+        wait_ld();
+        if (m < g.M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = cb + 4 * q;
+            float o[4];
+            const float4 b4 = bq[q];
+            o[0] = __uint_as_float(v[4 * q]) + b4.x; o[1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+            o[2] = __uint_as_float(v[4 * q + 2]) + b4.z; o[3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+            if (g.ln_gamma) {
+              const float4 ga = *reinterpret_cast<const float4*>(s_gamma + n), be = *reinterpret_cast<const float4*>(s_beta + n);
+              o[0] = fmaxf(fmaf((o[0] - mean) * rstd, ga.x, be.x), 0.f); o[1] = fmaxf(fmaf((o[1] - mean) * rstd, ga.y, be.y), 0.f);
+              o[2] = fmaxf(fmaf((o[2] - mean) * rstd, ga.z, be.z), 0.f); o[3] = fmaxf(fmaf((o[3] - mean) * rstd, ga.w, be.w), 0.f);
+            }
+            if (g.vec_c && n + 3 < g.N) {
+              float4* dst = reinterpret_cast<float4*>(crow + n);
+              if (g.accumulate) { const float4 p = *dst; o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w; }
+              *dst = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < g.N) crow[n + e] = g.accumulate ? crow[n + e] + o[e] : o[e];
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(bar + PB_ACC_FREE + ab);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<512>(tmem);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -367,6 +579,21 @@ int launch_tc_gemm(const TcGemmArgs& g_in, int n_batch, cudaStream_t st) {
       if (g.split3) tc_wsplit_kernel<3><<<sgrid, 256, 0, st>>>(g, n_chunks);
       else tc_wsplit_kernel<2><<<sgrid, 256, 0, st>>>(g, n_chunks);
     }
+  }
+  if (g.use_img && n_batch == 1 && g.N <= NT_MAX && g.M >= TM * device_sm_count()) {
+    // big GEMM with shared weights: persistent CTAs, epilogue of a tile under the main loop of the next
+    const int n_row_tiles = (g.M + TM - 1) / TM;
+    const int pgrid = n_row_tiles < device_sm_count() ? n_row_tiles : device_sm_count();
+    if (g.split3) {
+      static size_t configured_p[kMaxDevices] = {};
+      if (int rc = ensure_dynamic_smem(tc_gemm_persistent_kernel<3>, PCfg<3>::SMEM_TOTAL, configured_p)) return rc;
+      tc_gemm_persistent_kernel<3><<<pgrid, P_THREADS, PCfg<3>::SMEM_TOTAL, st>>>(g);
+    } else {
+      static size_t configured_p[kMaxDevices] = {};
+      if (int rc = ensure_dynamic_smem(tc_gemm_persistent_kernel<2>, PCfg<2>::SMEM_TOTAL, configured_p)) return rc;
+      tc_gemm_persistent_kernel<2><<<pgrid, P_THREADS, PCfg<2>::SMEM_TOTAL, st>>>(g);
+    }
+    return (int)cudaGetLastError();
   }
   if (g.split3) {
     static size_t configured[kMaxDevices] = {};
